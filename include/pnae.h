@@ -1,0 +1,116 @@
+/*
+ * pnae.h -- C ABI of the B200-native reconstruction-loss ops of pointnet-autoencoder.
+ *
+ * Drop-in boundary.  Each entry point replaces one C++-linkage host launcher that
+ * the reference's TensorFlow op glue calls (cited per function, paths relative to
+ * the reference root).  Conventions shared by all of them, mirroring the reference:
+ *   - plain pointers and ints only; every data pointer is a DEVICE pointer into
+ *     memory the CALLER owns (outputs and scratch included: the library never
+ *     allocates device memory and keeps no state between calls);
+ *   - row-major float32 point sets (b, n, 3) / (b, m, 3), int32 indices;
+ *   - outputs are fully overwritten (no pre-zeroing needed);
+ *   - the Chamfer entry points take (b, n, xyz1, m, xyz2, ...), the EMD ones
+ *     (b, n, m, xyz1, xyz2, ...) -- the reference's own argument-order quirk.
+ * What is new relative to the reference launchers:
+ *   - an explicit `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream, which is what the reference always used);
+ *   - an int status: 0 on success, a negative pnae_status otherwise, with a
+ *     thread-local message from pnae_last_error() (the reference checks nothing);
+ *   - caller-provided workspace where an op needs scratch (the reference's TF glue
+ *     did the same through allocate_temp, tf_approxmatch.cpp:168).
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * PNAE_ERR_CUDA.
+ */
+#ifndef PNAE_H_
+#define PNAE_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PNAE_API __attribute__((visibility("default")))
+#else
+#define PNAE_API
+#endif
+
+#define PNAE_VERSION 100          /* 0.1.0 */
+#define PNAE_NUM_LEVELS 10        /* j = 7..-2, tf_approxmatch_g.cu:21 */
+
+typedef enum pnae_status {
+    PNAE_OK = 0,
+    PNAE_ERR_INVALID_ARG = -1,    /* bad shape / NULL pointer / misaligned pointer */
+    PNAE_ERR_WORKSPACE = -2,      /* workspace too small */
+    PNAE_ERR_CUDA = -3,           /* launch or runtime failure; see pnae_last_error() */
+    PNAE_ERR_UNSUPPORTED = -4     /* device is not sm_100 */
+} pnae_status;
+
+PNAE_API int pnae_version(void);
+/* Message of the last failing call made on this thread ("" if none). */
+PNAE_API const char *pnae_last_error(void);
+/* SM count and compute capability of the current device. */
+PNAE_API int pnae_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- Chamfer distance -------------------------------------------------- */
+
+/* Scratch bytes pnae_nn_distance_fwd needs for these sizes (may be 0). */
+PNAE_API size_t pnae_nn_distance_workspace_bytes(int b, int n, int m);
+
+/* Replaces NmDistanceKernelLauncher (tf_ops/nn_distance/tf_nndistance_g.cu:128-131).
+ * dist1[i,j] = min_k |xyz1[i,j]-xyz2[i,k]|^2 (squared), idx1 = lowest-index argmin;
+ * dist2/idx2 the same with the roles swapped.  n, m >= 1. */
+PNAE_API int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                         float *dist1, int *idx1, float *dist2, int *idx2,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces NmDistanceGradKernelLauncher (tf_nndistance_g.cu:152-157).
+ * grad_xyz1 (b,n,3), grad_xyz2 (b,m,3); zeroed inside, like the reference. */
+PNAE_API int pnae_nn_distance_bwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                         const float *grad_dist1, const int *idx1,
+                         const float *grad_dist2, const int *idx2,
+                         float *grad_xyz1, float *grad_xyz2, void *stream);
+
+/* ---- approximate earth mover's distance -------------------------------- */
+
+/* Scratch bytes pnae_approx_match needs (the reference's `temp`, tf_approxmatch.cpp:168). */
+PNAE_API size_t pnae_approx_match_workspace_bytes(int b, int n, int m);
+
+/* Replaces approxmatchLauncher (tf_ops/approxmatch/tf_approxmatch_g.cu:180-182).
+ * xyz1 (b,n,3) "dataset", xyz2 (b,m,3) "query".
+ *   factors: (b, PNAE_NUM_LEVELS, n+m) float32, REQUIRED.  Per level the vectors
+ *            ratioL[0..n) then ratioR[0..m) of that level; they determine the soft
+ *            assignment completely:
+ *              match[i,l,k] = sum_j exp(level_j |xyz1[i,k]-xyz2[i,l]|^2) ratioL_j[k] ratioR_j[l]
+ *            (tf_approxmatch_g.cu:145-153 is the only write to `match`).
+ *   match:   (b, m, n) float32 or NULL.  The reference's dense output; pass NULL to
+ *            keep the b*m*n tensor out of HBM and feed `factors` to
+ *            pnae_match_cost_factors instead. */
+PNAE_API int pnae_approx_match(int b, int n, int m, const float *xyz1, const float *xyz2,
+                      float *factors, float *match,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Dense (b,m,n) match from the factors (same accumulation order as the reference). */
+PNAE_API int pnae_match_from_factors(int b, int n, int m, const float *xyz1, const float *xyz2,
+                            const float *factors, float *match, void *stream);
+
+/* Replaces matchcostLauncher (tf_approxmatch_g.cu:226-228): cost (b,) from a dense match. */
+PNAE_API int pnae_match_cost_fwd(int b, int n, int m, const float *xyz1, const float *xyz2,
+                        const float *match, float *cost, void *stream);
+
+/* Replaces matchcostgradLauncher (tf_approxmatch_g.cu:292-295): grad1 (b,n,3), grad2 (b,m,3)
+ * from a dense match (not yet scaled by the upstream grad_cost, as in the reference). */
+PNAE_API int pnae_match_cost_bwd(int b, int n, int m, const float *xyz1, const float *xyz2,
+                        const float *match, float *grad1, float *grad2, void *stream);
+
+/* matchcost + matchcostgrad in one pass straight from the factors; the dense
+ * tensor never exists.  grad1/grad2 may both be NULL (cost only). */
+PNAE_API int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, const float *xyz2,
+                            const float *factors, float *cost, float *grad1, float *grad2,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PNAE_H_ */

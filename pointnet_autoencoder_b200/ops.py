@@ -1,0 +1,185 @@
+"""Tensor-facing wrappers over the C ABI: shape validation (the reference's
+OP_REQUIRES conditions and messages), output allocation and the launch on torch's
+current stream.  torch is plumbing here (device memory + streams); all arithmetic
+happens in libpnae.so.  No CPU path: a non-CUDA tensor is an error.
+
+Reference glue being mirrored:
+  NnDistanceGpuOp / NnDistanceGradGpuOp      tf_ops/nn_distance/tf_nndistance.cpp:169-254
+  ApproxMatchGpuOp / MatchCostGpuOp / MatchCostGradGpuOp
+                                             tf_ops/approxmatch/tf_approxmatch.cpp:145-295
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+NUM_LEVELS = _lib.NUM_LEVELS
+
+
+def _require(cond, msg):
+    if not cond:
+        raise ValueError(msg)     # the reference raises errors::InvalidArgument(msg)
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: pointnet_autoencoder_b200 has no CPU path (CUDA tensors only)" % (name, t.device))
+    return t
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("expected float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _i32c(t):
+    if t.dtype != torch.int32:
+        raise TypeError("expected int32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_pair(op, xyz1, xyz2, style):
+    _dev(xyz1, "xyz1"); _dev(xyz2, "xyz2")
+    if style == "nn":
+        _require(xyz1.dim() == 3, "%s requires xyz1 be of shape (batch,#points,3)" % op)
+        _require(xyz1.shape[2] == 3, "%s only accepts 3d point set xyz1" % op)
+        _require(xyz2.dim() == 3, "%s requires xyz2 be of shape (batch,#points,3)" % op)
+        _require(xyz2.shape[2] == 3, "%s only accepts 3d point set xyz2" % op)
+        _require(xyz2.shape[0] == xyz1.shape[0], "%s expects xyz1 and xyz2 have same batch size" % op)
+    else:
+        _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "%s expects (batch_size,num_points,3) xyz1 shape" % op)
+        _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0],
+                 "%s expects (batch_size,num_points,3) xyz2 shape, and batch_size must match" % op)
+    _require(xyz1.shape[1] >= 1 and xyz2.shape[1] >= 1, "%s needs at least one point per cloud" % op)
+    _require(xyz1.device == xyz2.device, "%s expects xyz1 and xyz2 on the same device" % op)
+    return _f32c(xyz1), _f32c(xyz2), xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+
+
+# ---------------------------------------------------------------------------
+# Chamfer
+# ---------------------------------------------------------------------------
+def nn_distance_fwd(xyz1, xyz2):
+    """NnDistance: -> dist1 (B,N) f32, idx1 (B,N) i32, dist2 (B,M) f32, idx2 (B,M) i32"""
+    xyz1, xyz2, b, n, m = _check_pair("NnDistance", xyz1, xyz2, "nn")
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+        idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev) if wsb else None
+        _lib.check(lib.pnae_nn_distance_fwd(b, n, _p(xyz1), m, _p(xyz2), _p(dist1), _p(idx1), _p(dist2), _p(idx2),
+                                            _p(ws), wsb, _stream(xyz1)))
+    return dist1, idx1, dist2, idx2
+
+
+def nn_distance_bwd(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
+    """NnDistanceGrad: -> grad_xyz1 (B,N,3), grad_xyz2 (B,M,3)"""
+    op = "NnDistanceGrad"
+    xyz1, xyz2, b, n, m = _check_pair(op, xyz1, xyz2, "nn")
+    _require(tuple(grad_dist1.shape) == (b, n), "%s requires grad_dist1 be of shape(batch,#points)" % op)
+    _require(tuple(idx1.shape) == (b, n), "%s requires idx1 be of shape(batch,#points)" % op)
+    _require(tuple(grad_dist2.shape) == (b, m), "%s requires grad_dist2 be of shape(batch,#points)" % op)
+    _require(tuple(idx2.shape) == (b, m), "%s requires idx2 be of shape(batch,#points)" % op)
+    g1 = _f32c(_dev(grad_dist1, "grad_dist1")); g2 = _f32c(_dev(grad_dist2, "grad_dist2"))
+    i1 = _i32c(_dev(idx1, "idx1")); i2 = _i32c(_dev(idx2, "idx2"))
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        o1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        o2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.pnae_nn_distance_bwd(b, n, _p(xyz1), m, _p(xyz2), _p(g1), _p(i1), _p(g2), _p(i2),
+                                            _p(o1), _p(o2), _stream(xyz1)))
+    return o1, o2
+
+
+# ---------------------------------------------------------------------------
+# approximate EMD
+# ---------------------------------------------------------------------------
+def approx_match_factors(xyz1, xyz2, dense=False):
+    """ApproxMatch: -> factors (B,10,N+M) [, match (B,M,N) if dense]"""
+    xyz1, xyz2, b, n, m = _check_pair("ApproxMatch", xyz1, xyz2, "emd")
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        factors = torch.empty((b, NUM_LEVELS, n + m), dtype=torch.float32, device=dev)
+        match = torch.empty((b, m, n), dtype=torch.float32, device=dev) if dense else None
+        wsb = lib.pnae_approx_match_workspace_bytes(b, n, m)
+        ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.pnae_approx_match(b, n, m, _p(xyz1), _p(xyz2), _p(factors), _p(match), _p(ws), wsb, _stream(xyz1)))
+    return (factors, match) if dense else factors
+
+
+def match_from_factors(xyz1, xyz2, factors):
+    xyz1, xyz2, b, n, m = _check_pair("ApproxMatch", xyz1, xyz2, "emd")
+    _require(tuple(factors.shape) == (b, NUM_LEVELS, n + m), "factors must be (batch_size,10,#dataset+#query)")
+    factors = _f32c(_dev(factors, "factors"))
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        match = torch.empty((b, m, n), dtype=torch.float32, device=dev)
+        _lib.check(lib.pnae_match_from_factors(b, n, m, _p(xyz1), _p(xyz2), _p(factors), _p(match), _stream(xyz1)))
+    return match
+
+
+def _check_match(op, match, b, n, m):
+    _dev(match, "match")
+    _require(match.dim() == 3 and match.shape[0] == b and match.shape[1] == m and match.shape[2] == n,
+             "%s expects (batch_size,#query,#dataset) match shape" % op)
+    return _f32c(match)
+
+
+def match_cost_dense_fwd(xyz1, xyz2, match):
+    """MatchCost over a dense (B,M,N) match: -> cost (B,)"""
+    xyz1, xyz2, b, n, m = _check_pair("MatchCost", xyz1, xyz2, "emd")
+    match = _check_match("MatchCost", match, b, n, m)
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        cost = torch.empty((b,), dtype=torch.float32, device=dev)
+        _lib.check(lib.pnae_match_cost_fwd(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(cost), _stream(xyz1)))
+    return cost
+
+
+def match_cost_dense_bwd(xyz1, xyz2, match):
+    """MatchCostGrad over a dense match: -> grad1 (B,N,3), grad2 (B,M,3) (unscaled)"""
+    xyz1, xyz2, b, n, m = _check_pair("MatchCostGrad", xyz1, xyz2, "emd")
+    match = _check_match("MatchCost", match, b, n, m)     # sic: the reference's message says MatchCost (tf_approxmatch.cpp:280)
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        g1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        g2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.pnae_match_cost_bwd(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(g1), _p(g2), _stream(xyz1)))
+    return g1, g2
+
+
+def match_cost_factors(xyz1, xyz2, factors, with_grad=True):
+    """MatchCost (+MatchCostGrad) straight from the factors: -> cost[, grad1, grad2]"""
+    xyz1, xyz2, b, n, m = _check_pair("MatchCost", xyz1, xyz2, "emd")
+    _require(tuple(factors.shape) == (b, NUM_LEVELS, n + m), "MatchCost expects (batch_size,10,#dataset+#query) factors")
+    factors = _f32c(_dev(factors, "factors"))
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        cost = torch.empty((b,), dtype=torch.float32, device=dev)
+        g1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev) if with_grad else None
+        g2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev) if with_grad else None
+        _lib.check(lib.pnae_match_cost_factors(b, n, m, _p(xyz1), _p(xyz2), _p(factors), _p(cost), _p(g1), _p(g2), _stream(xyz1)))
+    return (cost, g1, g2) if with_grad else cost

@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA path (through the C ABI / the tf_ops-named Python API)
+against the CPU oracle on the same seeded inputs, and -- where the prebuilt
+oracle/_ref/libref_gpu.so travelled to this box -- against the reference's own
+CUDA kernels.  Tolerances are the north-star's: dist / match_cost 1e-5 relative,
+gradients 1e-4, idx bit-exact (near-ties are counted and bounded, not ignored).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from pointnet_autoencoder_b200 import ops, synthetic
+from pointnet_autoencoder_b200.tf_ops.approxmatch import tf_approxmatch
+from pointnet_autoencoder_b200.tf_ops.nn_distance import tf_nndistance
+
+pytestmark = pytest.mark.gpu
+O = oracle.cpu
+have_ref_gpu = oracle.ref_gpu.available()
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def clouds(gen, b, n, m, seed=7):
+    if gen == "randn":
+        return synthetic.s_randn(b, n, m, seed=seed)
+    label, pred = synthetic.s_chair(b, max(n, m))
+    return np.ascontiguousarray(label[:, :n]), np.ascontiguousarray(pred[:, :m])
+
+
+NN_CASES = [("randn", 2, 64, 64), ("randn", 1, 5, 6), ("randn", 3, 200, 37), ("randn", 2, 513, 1030),
+            ("chair", 2, 512, 512), ("randn", 1, 1, 1), ("randn", 2, 1, 700), ("randn", 33, 40, 50),
+            ("chair", 2, 2048, 2048), ("randn", 1, 3072, 2048), ("randn", 2, 64, 2048)]
+
+
+@pytest.mark.parametrize("gen,b,n,m", NN_CASES)
+def test_nn_distance_fwd_bit_exact_vs_oracle(gen, b, n, m):
+    xyz1, xyz2 = clouds(gen, b, n, m)
+    d1, i1, d2, i2 = [t.cpu().numpy() for t in tf_nndistance.nn_distance(cu(xyz1), cu(xyz2))]
+    od1, oi1, od2, oi2 = O.nn_distance(xyz1, xyz2, contract=True)
+    assert d1.dtype == np.float32 and i1.dtype == np.int32 and d1.shape == (b, n) and i2.shape == (b, m)
+    # integer/index work and fp32 with a pinned operation order: bit-exact
+    assert np.array_equal(d1, od1) and np.array_equal(d2, od2)
+    assert np.array_equal(i1, oi1) and np.array_equal(i2, oi2)
+
+
+def test_nn_distance_ties_and_self():
+    xyz2 = np.zeros((1, 8, 3), np.float32); xyz2[0, :, 0] = [5, 1, 1, 3, 1, 7, 0.5, 0.5]
+    xyz1 = np.zeros((1, 2, 3), np.float32); xyz1[0, 0, 0] = 1.0; xyz1[0, 1, 0] = 0.5
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(cu(xyz1), cu(xyz2))
+    assert i1.cpu().tolist() == [[1, 6]] and d1.cpu().tolist() == [[0.0, 0.0]]
+    a, _ = synthetic.s_randn(2, 777, 1, seed=5)
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(cu(a), cu(a))
+    assert (d1 == 0).all() and (d2 == 0).all()
+    ar = torch.arange(777, device="cuda", dtype=torch.int32)[None]
+    assert (i1 == ar).all() and (i2 == ar).all()
+
+
+@pytest.mark.parametrize("gen,b,n,m", [("randn", 2, 64, 64), ("randn", 3, 200, 37), ("chair", 2, 512, 512),
+                                       ("randn", 2, 1, 700), ("chair", 4, 2048, 2048)])
+def test_nn_distance_grad_vs_oracle(gen, b, n, m):
+    xyz1, xyz2 = clouds(gen, b, n, m)
+    rs = np.random.RandomState(3)
+    g1 = rs.randn(b, n).astype(np.float32); g2 = rs.randn(b, m).astype(np.float32)
+    x1 = cu(xyz1).requires_grad_(True); x2 = cu(xyz2).requires_grad_(True)
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(x1, x2)
+    (d1 * cu(g1)).sum().add((d2 * cu(g2)).sum()).backward()
+    o1, o2 = O.nn_distance_grad(xyz1, xyz2, g1, i1.cpu().numpy(), g2, i2.cpu().numpy())
+    # float atomics: the scatter half sums in a different order -> 1e-4 relative (north star), tiny atol
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), o1, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), o2, rtol=1e-4, atol=1e-5)
+
+
+def test_nn_distance_chamfer_loss_grad_constant():
+    # models/model.py:81-83: loss = 100*mean(dist1+dist2) -> upstream grad 100/(B*N)
+    label, pred = synthetic.s_chair(2, 1024)
+    x2 = cu(pred).requires_grad_(True)
+    d1, _, d2, _ = tf_nndistance.nn_distance(cu(label), x2)
+    loss = (d1 + d2).mean() * 100
+    loss.backward()
+    _, oi1, _, oi2 = O.nn_distance(label, pred)
+    g = np.full((2, 1024), 100.0 / (2 * 1024), np.float32)
+    _, o2 = O.nn_distance_grad(label, pred, g, oi1, g, oi2)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), o2, rtol=1e-4, atol=1e-7)
+
+
+EMD_CASES = [("chair", 2, 128, 128), ("chair", 2, 200, 50), ("chair", 1, 64, 256), ("randn", 2, 96, 96),
+             ("chair", 3, 300, 300), ("chair", 1, 1, 1), ("chair", 2, 1024, 1024), ("chair", 1, 400, 100)]
+
+
+@pytest.mark.parametrize("gen,b,n,m", EMD_CASES)
+def test_approx_match_and_cost_vs_oracle(gen, b, n, m):
+    xyz1, xyz2 = clouds(gen, b, n, m)
+    omatch, ofac = O.approx_match(xyz1, xyz2, dense=True, factors=True)
+    ocost = O.match_cost(xyz1, xyz2, omatch)
+    og1, og2 = O.match_cost_grad(xyz1, xyz2, omatch)
+
+    x1 = cu(xyz1).requires_grad_(True); x2 = cu(xyz2).requires_grad_(True)
+    match = tf_approxmatch.approx_match(x1, x2)
+    assert tuple(match.shape) == (b, m, n)
+    cost = tf_approxmatch.match_cost(x1, x2, match)
+    # model_emd.py:87: loss = mean(cost)
+    cost.mean().backward()
+    scale = max(1.0, float(n) / m if n >= m else 1.0)
+    np.testing.assert_allclose(match.factors.cpu().numpy(), ofac, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(match.dense().cpu().numpy(), omatch, rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(cost.detach().cpu().numpy(), ocost, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(x1.grad.cpu().numpy() * b, og1, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(x2.grad.cpu().numpy() * b, og2, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("gen,b,n,m", [("chair", 2, 128, 128), ("chair", 2, 200, 50), ("chair", 1, 333, 517)])
+def test_dense_match_path_vs_oracle(gen, b, n, m):
+    xyz1, xyz2 = clouds(gen, b, n, m)
+    omatch = O.approx_match(xyz1, xyz2)
+    x1 = cu(xyz1).requires_grad_(True); x2 = cu(xyz2).requires_grad_(True)
+    dense = tf_approxmatch.approx_match(x1, x2, dense=True)
+    assert isinstance(dense, torch.Tensor) and tuple(dense.shape) == (b, m, n)
+    scale = max(1.0, float(n) / m if n >= m else 1.0)
+    np.testing.assert_allclose(dense.cpu().numpy(), omatch, rtol=0, atol=2e-5 * scale)
+    # feed the ORACLE's dense match so only match_cost / match_cost_grad are under test
+    mt = cu(omatch)
+    cost = tf_approxmatch.match_cost(x1, x2, mt)
+    cost.sum().backward()
+    np.testing.assert_allclose(cost.detach().cpu().numpy(), O.match_cost(xyz1, xyz2, omatch), rtol=1e-5)
+    og1, og2 = O.match_cost_grad(xyz1, xyz2, omatch)
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), og1, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), og2, rtol=1e-4, atol=2e-6)
+
+
+def test_match_handle_is_tensor_like_and_guards_constant_semantics():
+    xyz1, xyz2 = clouds("chair", 2, 128, 128)
+    x1 = cu(xyz1); x2 = cu(xyz2)
+    match = tf_approxmatch.approx_match(x1, x2)
+    s = torch.sum(match, dim=1)          # torch function on the handle -> densified
+    np.testing.assert_allclose(s.cpu().numpy(), 1.0, rtol=2e-4)
+    assert match[0].shape == (128, 128)
+    # different clouds than the match was computed from -> must behave as a constant dense match
+    y1 = x1 + 0.01
+    c_handle = tf_approxmatch.match_cost(y1, x2, match)
+    c_dense = tf_approxmatch.match_cost(y1, x2, match.dense())
+    assert torch.equal(c_handle, c_dense)
+
+
+def test_full_size_properties():
+    # BASELINE config: B=32, N=M=2048 -- size-independent properties instead of the (slow) oracle
+    label, pred = synthetic.s_chair(32, 2048)
+    x1 = cu(label); x2 = cu(pred)
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(x1, x2)
+    # (1) the reported neighbour really is at the reported distance, (2) no candidate is closer (sampled)
+    g = torch.gather(x2, 1, i1.long()[:, :, None].expand(-1, -1, 3))
+    diff = g - x1
+    rec = torch.addcmul(torch.addcmul(diff[..., 1] * diff[..., 1], diff[..., 0], diff[..., 0]), diff[..., 2], diff[..., 2])
+    assert torch.allclose(rec, d1, rtol=1e-6, atol=0)
+    full = torch.cdist(x1[:2].double(), x2[:2].double()) ** 2
+    assert torch.allclose(full.min(2).values.float(), d1[:2], rtol=1e-5, atol=1e-9)
+    assert torch.allclose(full.min(1).values.float(), d2[:2], rtol=1e-5, atol=1e-9)
+    # EMD: rows and columns of the soft assignment sum to 1 (n == m); cost(x,x) is ~0 relative to cost(x,y)
+    match = tf_approxmatch.approx_match(x1, x2)
+    dense = match.dense()
+    assert dense.shape == (32, 2048, 2048) and (dense >= 0).all()
+    assert torch.allclose(dense.sum(1), torch.ones(32, 2048, device="cuda"), rtol=0, atol=5e-4)
+    assert torch.allclose(dense.sum(2), torch.ones(32, 2048, device="cuda"), rtol=0, atol=5e-4)
+    cost = tf_approxmatch.match_cost(x1, x2, match)
+    cost_dense = tf_approxmatch.match_cost(x1, x2, dense)
+    assert torch.allclose(cost, cost_dense, rtol=1e-5)
+    # sharded == unsharded (the multi-GPU split is a batch slice)
+    half = tf_approxmatch.match_cost(x1[16:], x2[16:], tf_approxmatch.approx_match(x1[16:].contiguous(), x2[16:].contiguous()))
+    assert torch.equal(half, cost[16:])
+
+
+def test_validation_errors_mirror_reference_messages():
+    a = torch.zeros(2, 8, 3, device="cuda"); b4 = torch.zeros(2, 8, 4, device="cuda"); c = torch.zeros(3, 8, 3, device="cuda")
+    with pytest.raises(ValueError, match="NnDistance only accepts 3d point set xyz2"):
+        tf_nndistance.nn_distance(a, b4)
+    with pytest.raises(ValueError, match="NnDistance expects xyz1 and xyz2 have same batch size"):
+        tf_nndistance.nn_distance(a, c)
+    with pytest.raises(ValueError, match="NnDistance requires xyz1 be of shape"):
+        tf_nndistance.nn_distance(a[0], a)
+    with pytest.raises(ValueError, match="ApproxMatch expects .* xyz2 shape, and batch_size must match"):
+        tf_approxmatch.approx_match(a, c)
+    with pytest.raises(ValueError, match="MatchCost expects .*match shape"):
+        tf_approxmatch.match_cost(a, a, torch.zeros(2, 8, 7, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        tf_nndistance.nn_distance(a.cpu(), a.cpu())
+
+
+@pytest.mark.skipif(not have_ref_gpu, reason="oracle/_ref/libref_gpu.so not present")
+class TestAgainstReferenceKernels:
+    """The reference's own .cu files, compiled unmodified for sm_100a, on this GPU."""
+
+    def test_levels_are_exact_powers_of_four(self):
+        lv = oracle.ref_gpu.levels()
+        assert lv.tolist() == [-16384.0, -4096.0, -1024.0, -256.0, -64.0, -16.0, -4.0, -1.0, -0.25, 0.0]
+
+    @pytest.mark.parametrize("gen,b,n,m", [("randn", 4, 1000, 777), ("chair", 32, 2048, 2048), ("randn", 2, 16384, 1024)])
+    def test_nn_distance_bit_exact(self, gen, b, n, m):
+        xyz1, xyz2 = clouds(gen, b, n, m)
+        x1 = cu(xyz1); x2 = cu(xyz2)
+        mine = tf_nndistance.nn_distance(x1, x2)
+        ref = oracle.ref_gpu.nn_distance(x1, x2)
+        for a, r in zip(mine, ref):
+            assert torch.equal(a, r)
+
+    @pytest.mark.parametrize("gen,b,n,m", [("randn", 4, 1000, 777), ("chair", 8, 2048, 2048)])
+    def test_nn_distance_grad(self, gen, b, n, m):
+        xyz1, xyz2 = clouds(gen, b, n, m)
+        x1 = cu(xyz1); x2 = cu(xyz2)
+        _, i1, _, i2 = tf_nndistance.nn_distance(x1, x2)
+        g1 = torch.randn(b, n, device="cuda"); g2 = torch.randn(b, m, device="cuda")
+        m1, m2 = tf_nndistance.nn_distance_grad(x1, x2, g1, i1, g2, i2)
+        r1, r2 = oracle.ref_gpu.nn_distance_grad(x1, x2, g1, i1, g2, i2)
+        assert torch.allclose(m1, r1, rtol=1e-4, atol=1e-5) and torch.allclose(m2, r2, rtol=1e-4, atol=1e-5)
+
+    @pytest.mark.parametrize("gen,b,n,m", [("chair", 4, 512, 512), ("chair", 2, 400, 100), ("chair", 2, 2048, 2048), ("randn", 2, 1024, 1024)])
+    def test_emd(self, gen, b, n, m):
+        xyz1, xyz2 = clouds(gen, b, n, m)
+        x1 = cu(xyz1); x2 = cu(xyz2)
+        rmatch = oracle.ref_gpu.approx_match(x1, x2)
+        rcost = oracle.ref_gpu.match_cost(x1, x2, rmatch)
+        rg1, rg2 = oracle.ref_gpu.match_cost_grad(x1, x2, rmatch)
+        match = tf_approxmatch.approx_match(x1, x2)
+        scale = max(1.0, float(n) / m if n >= m else 1.0)
+        assert torch.allclose(match.dense(), rmatch, rtol=0, atol=2e-5 * scale)
+        cost, g1, g2 = ops.match_cost_factors(x1, x2, match.factors)
+        assert torch.allclose(cost, rcost, rtol=1e-5)
+        assert torch.allclose(g1, rg1, rtol=1e-4, atol=2e-5) and torch.allclose(g2, rg2, rtol=1e-4, atol=2e-5)
+        # dense-path kernels on the reference's own match
+        assert torch.allclose(ops.match_cost_dense_fwd(x1, x2, rmatch), rcost, rtol=1e-5)
+        d1, d2 = ops.match_cost_dense_bwd(x1, x2, rmatch)
+        assert torch.allclose(d1, rg1, rtol=1e-4, atol=2e-6) and torch.allclose(d2, rg2, rtol=1e-4, atol=2e-6)

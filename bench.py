@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json configs[1]):
+nn_distance forward + gradient at B=32, N=M=2048 per GPU, in G unordered pairs/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the Chamfer hot path (NnDistance + NnDistanceGrad through
+the C ABI) over one batch of synthetic clouds.  Prints ONE JSON line on rank 0.
+See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, N, M = 32, 2048, 2048
+METRIC = "nn_distance_fwd_grad_throughput"
+UNIT = "Gpairs/s"            # unordered (xyz1 point, xyz2 point) pairs: B*N*M per step
+FLOP_PER_PAIR = 16           # algorithmic: 2 directed evaluations x 8 FLOP (tf_nndistance_g.cu:25-28)
+RING = 64                    # distinct batches cycled through, so the working set exceeds the 126 MB L2
+
+
+def make_inputs(b, n, m, ring, seed=100):
+    """S-randn (mirrors tf_nndistance.py:45-49), `ring` independent batches."""
+    rs = np.random.RandomState(seed)
+    xyz1 = rs.randn(ring, b, n, 3).astype(np.float32)
+    xyz2 = rs.randn(ring, b, m, 3).astype(np.float32)
+    return xyz1, xyz2
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [s for (t, s) in self.samples if t0 - 0.05 <= t <= t1 + 0.05] or [s for (_, s) in self.samples]
+        mhz, mx, reasons = [], None, set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline  (the only places oracle/ is executed here)
+# ---------------------------------------------------------------------------
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _ref_cpu_step(lib, xyz1, xyz2, g1, g2, threads):
+    """One fwd+grad pass of the reference's CPU loops over a (b,n,3)/(b,m,3) batch,
+    batch elements split over `threads` host threads (the reference itself is single-threaded)."""
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    d1 = np.empty((b, n), np.float32); i1 = np.empty((b, n), np.int32)
+    d2 = np.empty((b, m), np.float32); i2 = np.empty((b, m), np.int32)
+    o1 = np.empty((b, n, 3), np.float32); o2 = np.empty((b, m, 3), np.float32)
+    fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
+
+    def work(lo, hi):
+        if hi <= lo:
+            return
+        s = slice(lo, hi)
+        args = (hi - lo, n, xyz1[s].ctypes.data_as(fp), m, xyz2[s].ctypes.data_as(fp))
+        lib.ref_cpu_nn_distance(*args, d1[s].ctypes.data_as(fp), i1[s].ctypes.data_as(ip),
+                                d2[s].ctypes.data_as(fp), i2[s].ctypes.data_as(ip))
+        lib.ref_cpu_nn_distance_grad(*args, g1[s].ctypes.data_as(fp), i1[s].ctypes.data_as(ip),
+                                     g2[s].ctypes.data_as(fp), i2[s].ctypes.data_as(ip),
+                                     o1[s].ctypes.data_as(fp), o2[s].ctypes.data_as(fp))
+    if threads <= 1:
+        work(0, b)
+    else:
+        bounds = np.linspace(0, b, threads + 1).astype(int)
+        ths = [threading.Thread(target=work, args=(bounds[t], bounds[t + 1])) for t in range(threads)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    return d1, i1, d2, i2, o1, o2
+
+
+def _load_ref_cpu():
+    """oracle/_ref/libref_cpu.so (the reference's own loops) if it is there, else the oracle port."""
+    import oracle
+    if oracle.ref_cpu.available():
+        return oracle.ref_cpu.lib, "reference"
+    lib = oracle.cpu.lib
+
+    class Port:   # same entry-point names over the C restatement
+        @staticmethod
+        def ref_cpu_nn_distance(b, n, x1, m, x2, d1, i1, d2, i2):
+            lib.oracle_nn_distance(b, n, x1, m, x2, d1, i1, d2, i2, 0)
+
+        @staticmethod
+        def ref_cpu_nn_distance_grad(*a):
+            lib.oracle_nn_distance_grad(*a)
+    return Port, "port"
+
+
+def cpu_baseline(threads, reps, sample_b=None):
+    lib, kind = _load_ref_cpu()
+    b = sample_b or B
+    xyz1, xyz2 = make_inputs(b, N, M, 1)
+    g1 = np.full((b, N), 100.0 / (b * N), np.float32); g2 = np.full((b, M), 100.0 / (b * M), np.float32)
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _ref_cpu_step(lib, xyz1[0], xyz2[0], g1, g2, threads)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": b * N * M / best / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "fwd+grad on %d of %d batch elements (N=M=%d), best of %d, %s" % (b, B, N, reps, _cpu_model()),
+            "seconds_per_step_sample": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    lib, kind = _load_ref_cpu()
+    xyz1, xyz2 = make_inputs(B, N, M, 1)
+    g1 = np.full((B, N), 100.0 / (B * N), np.float32); g2 = np.full((B, M), 100.0 / (B * M), np.float32)
+    for _ in range(args.warmup):
+        _ref_cpu_step(lib, xyz1[0], xyz2[0], g1, g2, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _ref_cpu_step(lib, xyz1[0], xyz2[0], g1, g2, threads)
+    dt = time.perf_counter() - t0
+    val = B * N * M * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (S-randn, seed 100)",
+            "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d (BASELINE.json configs[1]) on the host CPU" % (B, N),
+                       "note": "reference CPU loops (tf_nndistance.cpp:21-43,126-163); the reference is single-threaded, "
+                               "here the batch is split over all host threads"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "full batch, every step, %s" % _cpu_model()},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from pointnet_autoencoder_b200 import _lib, ops
+    from pointnet_autoencoder_b200 import host_api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    sms = C.c_int(); maj = C.c_int(); mnr = C.c_int()
+    _lib.check(lib.pnae_device_info(C.byref(sms), C.byref(maj), C.byref(mnr)))
+
+    # each rank owns its own B elements (batch sharding, no data-path collective): weak scaling
+    h1, h2 = make_inputs(B, N, M, RING, seed=100 + rank)
+    x1 = torch.from_numpy(h1).to(dev); x2 = torch.from_numpy(h2).to(dev)
+    g1 = torch.full((B, N), 100.0 / (B * N), device=dev); g2 = torch.full((B, M), 100.0 / (B * M), device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        a = x1[i % RING]; c = x2[i % RING]
+        d1, i1, d2, i2 = ops.nn_distance_fwd(a, c)
+        return ops.nn_distance_bwd(a, c, g1, i1, g2, i2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    # kernel-only events for the dominant kernel (the forward), on the launching stream
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        a = x1[i % RING]; c = x2[i % RING]
+        fwd_ev[i][0].record(stream)
+        d1, i1, d2, i2 = ops.nn_distance_fwd(a, c)
+        fwd_ev[i][1].record(stream)
+        ops.nn_distance_bwd(a, c, g1, i1, g2, i2)
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    ms = e0.elapsed_time(e1)
+    fwd_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in fwd_ev]))
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end through the public host-buffer API: pinned host in, results back on the host
+    e2e_steps = max(10, min(args.steps, 50))
+    runner = host_api.ChamferHostRunner(B, N, M, dev)
+    p1 = torch.from_numpy(h1).pin_memory(); p2 = torch.from_numpy(h2).pin_memory()   # inputs start in pinned host memory
+    for i in range(3):
+        runner.step(p1[i % RING], p2[i % RING])
+    barrier()
+    e2e0 = time.perf_counter()
+    for i in range(e2e_steps):
+        runner.step(p1[i % RING], p2[i % RING])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e2e0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs = B * N * M
+    value = pairs * args.steps * world / (ms * 1e-3) / 1e9
+    sm_max = clocks.get("sm_max_mhz") or 1965.0
+    fp32_peak = sms.value * 128 * 2 * sm_max * 1e6 / 1e12          # TFLOP/s at the max SM clock
+    achieved = FLOP_PER_PAIR * pairs / (fwd_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (OSError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = 4 * (3 * B * (N + M) + 2 * B * (N + M))               # xyz in, dist+idx out
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (S-randn, seed 100+rank; mirrors tf_nndistance.py:45-49)",
+        "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
+                   "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
+                   "l2": "ring of %d distinct batches (%.0f MB touched) > 126 MB L2" % (RING, RING * (alg_bytes + 12 * B * (N + M)) / 1e6),
+                   "upstream_grad": "100/(B*N) (models/model.py:81-83)"},
+        "roofline": {"bound": "fp32", "kernel": "nn_distance forward", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak, "traffic": None,
+                     "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/)" % (sms.value, sm_max),
+                     "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
+                     "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "e2e": {"value": pairs * e2e_steps * world / e2e_s / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(threads=1, reps=3)
+    if world == 1 and not args.no_emd:
+        line["extra"] = emd_numbers(dev)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def emd_numbers(dev):
+    """BASELINE.json's second figure: approx_match ms (and EMD fwd+grad ms) at B=32 N=2048."""
+    import torch
+    from pointnet_autoencoder_b200 import ops, synthetic
+    label, pred = synthetic.s_chair(B, N)
+    x1 = torch.from_numpy(label).to(dev); x2 = torch.from_numpy(pred).to(dev)
+
+    def t(fn, it=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(it):
+            a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b_.record(); b_.synchronize()
+            ts.append(a.elapsed_time(b_))
+        return float(np.median(ts))
+    fac = ops.approx_match_factors(x1, x2)
+    am = t(lambda: ops.approx_match_factors(x1, x2))
+    mc = t(lambda: ops.match_cost_factors(x1, x2, fac))
+    peak = 148 * 128 * 2 * 1.965e9
+    pairs = B * N * N
+    return {"approx_match_ms": am, "match_cost_fwd_grad_ms": mc, "emd_fwd_grad_ms": am + mc,
+            "emd_frac_of_fp32_peak": 423 * pairs / ((am + mc) * 1e-3) / peak, "data": "S-chair"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-emd", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+"""Host-buffer entry points: numpy / pinned host arrays in, numpy out.
+
+This is the call a user without device tensors makes (and what bench.py's `e2e`
+figure times): every step copies its inputs host->device, runs the kernels through
+the C ABI and copies the results device->host.  Buffers (pinned staging, device
+inputs/outputs) are allocated once per runner and reused.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _pinned(shape, dtype):
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+class ChamferHostRunner:
+    """NnDistance + NnDistanceGrad for fixed (B, N, M) with host buffers.
+
+    step(xyz1, xyz2[, grad_dist1, grad_dist2]) -> dict of numpy views on pinned
+    result buffers (valid until the next step).  Default upstream gradient is the
+    Chamfer loss's constant 100/(B*N) (models/model.py:81-83)."""
+
+    def __init__(self, b, n, m, device="cuda"):
+        self.b, self.n, self.m = b, n, m
+        self.device = torch.device(device)
+        self.h_xyz1 = _pinned((b, n, 3), torch.float32); self.h_xyz2 = _pinned((b, m, 3), torch.float32)
+        self.d_xyz1 = torch.empty((b, n, 3), dtype=torch.float32, device=self.device)
+        self.d_xyz2 = torch.empty((b, m, 3), dtype=torch.float32, device=self.device)
+        self.g1 = torch.full((b, n), 100.0 / (b * n), device=self.device)
+        self.g2 = torch.full((b, m), 100.0 / (b * m), device=self.device)
+        self.h_out = {
+            "dist1": _pinned((b, n), torch.float32), "idx1": _pinned((b, n), torch.int32),
+            "dist2": _pinned((b, m), torch.float32), "idx2": _pinned((b, m), torch.int32),
+            "grad_xyz1": _pinned((b, n, 3), torch.float32), "grad_xyz2": _pinned((b, m, 3), torch.float32),
+        }
+        self.h2d_bytes = 4 * 3 * b * (n + m)
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
+
+    def _stage(self, src, pinned):
+        if isinstance(src, torch.Tensor):
+            if src.is_pinned():
+                return src
+            pinned.copy_(src)
+            return pinned
+        pinned.numpy()[...] = src
+        return pinned
+
+    def step(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None):
+        with torch.cuda.device(self.device):
+            self.d_xyz1.copy_(self._stage(xyz1, self.h_xyz1), non_blocking=True)
+            self.d_xyz2.copy_(self._stage(xyz2, self.h_xyz2), non_blocking=True)
+            g1 = self.g1 if grad_dist1 is None else torch.as_tensor(grad_dist1, dtype=torch.float32).to(self.device)
+            g2 = self.g2 if grad_dist2 is None else torch.as_tensor(grad_dist2, dtype=torch.float32).to(self.device)
+            d1, i1, d2, i2 = ops.nn_distance_fwd(self.d_xyz1, self.d_xyz2)
+            o1, o2 = ops.nn_distance_bwd(self.d_xyz1, self.d_xyz2, g1, i1, g2, i2)
+            for k, t in (("dist1", d1), ("idx1", i1), ("dist2", d2), ("idx2", i2), ("grad_xyz1", o1), ("grad_xyz2", o2)):
+                self.h_out[k].copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in self.h_out.items()}
+
+
+def nn_distance_host(xyz1, xyz2, grad_dist1=None, grad_dist2=None):
+    """One-shot convenience wrapper: numpy in -> dict of numpy arrays (copies)."""
+    xyz1 = np.ascontiguousarray(xyz1, np.float32); xyz2 = np.ascontiguousarray(xyz2, np.float32)
+    r = ChamferHostRunner(xyz1.shape[0], xyz1.shape[1], xyz2.shape[1])
+    return {k: v.copy() for k, v in r.step(xyz1, xyz2, grad_dist1, grad_dist2).items()}
+
+
+def emd_host(xyz1, xyz2):
+    """approx_match + match_cost + gradient with host buffers: -> cost (B,), grad1, grad2 (numpy)."""
+    x1 = torch.from_numpy(np.ascontiguousarray(xyz1, np.float32)).cuda()
+    x2 = torch.from_numpy(np.ascontiguousarray(xyz2, np.float32)).cuda()
+    fac = ops.approx_match_factors(x1, x2)
+    cost, g1, g2 = ops.match_cost_factors(x1, x2, fac)
+    return cost.cpu().numpy(), g1.cpu().numpy(), g2.cpu().numpy()

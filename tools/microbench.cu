@@ -59,6 +59,52 @@ __global__ void __launch_bounds__(256) kern(float *out, float a, float b, int it
                 for (int q = 0; q < 3; q++) acc2[i] = __ffma2_rn(acc2[i], a2, b2);
                 float r, s; asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(acc[i]), "f"(acc2[i].x), "f"(acc2[i].y));
                 asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(s) : "f"(a), "f"(acc2[i].x), "f"(acc2[i].y)); acc[i] = r + s * 0.f; }
+            if (MODE == 16) { float r; asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc[i]), "f"(a)); acc[i] = r; }   // FMNMX
+            if (MODE == 17 || MODE == 18) {  // 6 FFMA + 1|2 FMNMX
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc[i] = __fmaf_rn(acc[i], a, b);
+                float r; asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc2[i].x), "f"(acc[i])); acc2[i].x = r;
+                if (MODE == 18) { asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc2[i].y), "f"(acc[i])); acc2[i].y = r; } }
+            if (MODE == 19) {  // 6 FFMA + compare/select pair (the reference's argmin update)
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc[i] = __fmaf_rn(acc[i], a, b);
+                if (acc[i] < acc2[i].x) { acc2[i].x = acc[i]; uacc[i] = it; } }
+            if (MODE == 20) {  // 6 FFMA + 1 IADD3 (does the ALU pipe co-issue for free?)
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc[i] = __fmaf_rn(acc[i], a, b);
+                unsigned r; asm volatile("add.u32 %0, %1, %2;" : "=r"(r) : "r"(uacc[i]), "r"(it)); uacc[i] = r; }
+            if (MODE == 21) {  // 6 FFMA + 2 integer min (d >= 0: u32 order == float order)
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc[i] = __fmaf_rn(acc[i], a, b);
+                unsigned r; asm volatile("min.u32 %0, %1, %2;" : "=r"(r) : "r"(uacc[i]), "r"(__float_as_uint(acc[i]))); uacc[i] = r;
+                unsigned q2; asm volatile("min.u32 %0, %1, %2;" : "=r"(q2) : "r"(__float_as_uint(acc2[i].y)), "r"(__float_as_uint(acc[i]))); acc2[i].y = __uint_as_float(q2); }
+            if (MODE == 22) { uacc[i] = __vimin3_u32(uacc[i], (unsigned)it, __float_as_uint(a)); }   // VIMNMX3
+            if (MODE == 23) {  // EMD mix per 2 pairs: 8 packed + 2 MUFU
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc2[i] = __ffma2_rn(acc2[i], a2, b2);
+                float r0, r1; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(acc2[i].x)); asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(acc2[i].y));
+                acc2[i] = make_float2(r0, r1); }
+            if (MODE == 24) {  // EMD mix per pair, scalar: 8 FFMA-class + 1 MUFU is mode 11; here 9 + 1
+#pragma unroll
+                for (int q = 0; q < 9; q++) acc[i] = __fmaf_rn(acc[i], a, b);
+                float r; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(acc[i])); acc[i] = r; }
+            if (MODE == 25) {  // 6 FFMA2 + 2 MUFU
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc2[i] = __ffma2_rn(acc2[i], a2, b2);
+                float r0, r1; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(acc2[i].x)); asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(acc2[i].y));
+                acc2[i] = make_float2(r0, r1); }
+            if (MODE == 26) {  // 3 FFMA2 + 2 FMNMX (2-input) : Chamfer both directions, 2 pairs -> needs 4 mins; here 2
+#pragma unroll
+                for (int q = 0; q < 3; q++) acc2[i] = __ffma2_rn(acc2[i], a2, b2);
+                float r; asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc[i]), "f"(acc2[i].x)); acc[i] = r;
+                asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc[(i + 1) % NACC]), "f"(acc2[i].y)); acc[(i + 1) % NACC] = r; }
+            if (MODE == 27) {  // 3 FFMA2 + 4 FMNMX
+#pragma unroll
+                for (int q = 0; q < 3; q++) acc2[i] = __ffma2_rn(acc2[i], a2, b2);
+                float r; asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc[i]), "f"(acc2[i].x)); acc[i] = r;
+                asm volatile("min.f32 %0, %1, %2;" : "=f"(r) : "f"(acc[i]), "f"(acc2[i].y)); acc[i] = r;
+                unsigned u; asm volatile("min.u32 %0, %1, %2;" : "=r"(u) : "r"(uacc[i]), "r"(__float_as_uint(acc2[i].x))); uacc[i] = u;
+                asm volatile("min.u32 %0, %1, %2;" : "=r"(u) : "r"(uacc[i]), "r"(__float_as_uint(acc2[i].y))); uacc[i] = u; }
         }
     }
     float s = 0;
@@ -110,6 +156,18 @@ int main()
     run<13>("3 FFMA2 + 1 FMNMX3 (groups)", 1, sms, out);
     run<14>("6 FFMA + 1 FMNMX3 (groups)", 1, sms, out);
     run<15>("3 FFMA2 + 2 FMNMX3 (groups)", 1, sms, out);
+    run<16>("FMNMX", 1, sms, out);
+    run<17>("6 FFMA + 1 FMNMX (groups)", 1, sms, out);
+    run<18>("6 FFMA + 2 FMNMX (groups)", 1, sms, out);
+    run<19>("6 FFMA + cmp/sel/sel (grp)", 1, sms, out);
+    run<20>("6 FFMA + 1 IADD (groups)", 1, sms, out);
+    run<21>("6 FFMA + 2 IMNMX (groups)", 1, sms, out);
+    run<22>("VIMNMX3", 1, sms, out);
+    run<23>("8 FFMA2 + 2 MUFU (groups)", 1, sms, out);
+    run<24>("9 FFMA + 1 MUFU (groups)", 1, sms, out);
+    run<25>("6 FFMA2 + 2 MUFU (groups)", 1, sms, out);
+    run<26>("3 FFMA2 + 2 FMNMX (groups)", 1, sms, out);
+    run<27>("3 FFMA2 + 2FMNMX+2IMNMX", 1, sms, out);
     run<8>("REDUX.MIN", 1, sms, out);
     run<9>("SHFL", 1, sms, out);
     return 0;

@@ -113,7 +113,15 @@ def _ref_cpu_step(lib, xyz1, xyz2, g1, g2, threads):
     o1 = np.empty((b, n, 3), np.float32); o2 = np.empty((b, m, 3), np.float32)
     fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
 
+    errors = []
+
     def work(lo, hi):
+        try:
+            _work(int(lo), int(hi))
+        except BaseException as e:   # a silently dead thread would fake a fast baseline
+            errors.append(e)
+
+    def _work(lo, hi):
         if hi <= lo:
             return
         s = slice(lo, hi)
@@ -130,6 +138,8 @@ def _ref_cpu_step(lib, xyz1, xyz2, g1, g2, threads):
         ths = [threading.Thread(target=work, args=(bounds[t], bounds[t + 1])) for t in range(threads)]
         [t.start() for t in ths]
         [t.join() for t in ths]
+    if errors:
+        raise errors[0]
     return d1, i1, d2, i2, o1, o2
 
 

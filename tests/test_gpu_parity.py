@@ -18,6 +18,13 @@ O = oracle.cpu
 have_ref_gpu = oracle.ref_gpu.available()
 
 
+def close_scaled(a, ref, rel, what=""):
+    """max|a-ref| <= rel * max|ref|: "within rel" for a vector-valued result (a gradient field)"""
+    a = np.asarray(a, np.float64); ref = np.asarray(ref, np.float64)
+    err = np.abs(a - ref).max(); scale = max(np.abs(ref).max(), 1e-30)
+    assert err <= rel * scale, "%s max|diff| %.3e > %.1e * max|ref| %.3e" % (what, err, rel, scale)
+
+
 def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -86,7 +93,7 @@ def test_nn_distance_chamfer_loss_grad_constant():
 
 
 EMD_CASES = [("chair", 2, 128, 128), ("chair", 2, 200, 50), ("chair", 1, 64, 256), ("randn", 2, 96, 96),
-             ("chair", 3, 300, 300), ("chair", 1, 1, 1), ("chair", 2, 1024, 1024), ("chair", 1, 400, 100)]
+             ("chair", 3, 300, 300), ("randn", 1, 1, 1), ("chair", 2, 1024, 1024), ("chair", 1, 400, 100)]
 
 
 @pytest.mark.parametrize("gen,b,n,m", EMD_CASES)
@@ -113,8 +120,8 @@ def test_approx_match_and_cost_vs_oracle(gen, b, n, m):
     np.testing.assert_allclose(dm, omatch, rtol=0, atol=2e-4 * scale)
     assert np.abs(dm - omatch).mean() < 2e-7 * scale
     np.testing.assert_allclose(cost.detach().cpu().numpy(), ocost, rtol=1e-5, atol=1e-7)
-    np.testing.assert_allclose(x1.grad.cpu().numpy() * b, og1, rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(x2.grad.cpu().numpy() * b, og2, rtol=1e-4, atol=2e-5)
+    close_scaled(x1.grad.cpu().numpy() * b, og1, 1e-4, "grad1")
+    close_scaled(x2.grad.cpu().numpy() * b, og2, 1e-4, "grad2")
 
 
 @pytest.mark.parametrize("gen,b,n,m", [("chair", 2, 128, 128), ("chair", 2, 200, 50), ("chair", 1, 333, 517)])

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-fmad=true",   # every rounding-relevant contraction in the kernels is an explicit intrinsic
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-I", INCLUDE,
-]
+] + os.environ.get("PNAE_NVCC_DEFS", "").split()   # tuning experiments only, e.g. PNAE_NVCC_DEFS="-DPNAE_NN_COLS=128"
 
 
 def _sources():

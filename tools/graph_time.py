@@ -1,0 +1,61 @@
+"""Kernel-only timing: capture `reps` back-to-back calls of one op in a CUDA graph and
+replay it, so host launch overhead is out of the picture.
+    python tools/graph_time.py [B N M]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from pointnet_autoencoder_b200 import ops, synthetic
+
+
+def graph_time(fn, reps=20):
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    for _ in range(20):
+        g.replay()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) / (n * reps)
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    b, n, m = (int(args[0]), int(args[1]), int(args[2])) if len(args) >= 3 else (32, 2048, 2048)
+    x1n, x2n = synthetic.s_randn(b, n, m)
+    x1 = torch.from_numpy(x1n).cuda(); x2 = torch.from_numpy(x2n).cuda()
+    pairs = b * n * m
+    peak = 148 * 128 * 2 * 1.965e9
+    d1, i1, d2, i2 = ops.nn_distance_fwd(x1, x2)
+    g1 = torch.full((b, n), 100.0 / (b * n), device="cuda"); g2 = torch.full((b, m), 100.0 / (b * m), device="cuda")
+    t = graph_time(lambda: ops.nn_distance_fwd(x1, x2))
+    print("nn_distance fwd  %8.2f us  %5.1f%% of fp32 peak (16 flop/pair)" % (t * 1e3, 100 * 16 * pairs / (t * 1e-3) / peak))
+    t2 = graph_time(lambda: ops.nn_distance_bwd(x1, x2, g1, i1, g2, i2))
+    print("nn_distance bwd  %8.2f us" % (t2 * 1e3))
+    print("fwd+bwd          %8.2f us  %5.1f%% of fp32 peak  %.0f Gpairs/s" % ((t + t2) * 1e3, 100 * 16 * pairs / ((t + t2) * 1e-3) / peak, pairs / ((t + t2) * 1e-3) / 1e9))
+    if "--emd" in sys.argv:
+        fac = ops.approx_match_factors(x1, x2)
+        t = graph_time(lambda: ops.approx_match_factors(x1, x2), reps=2)
+        print("approx_match     %8.2f us  %5.1f%% of fp32 peak (380 flop/pair)" % (t * 1e3, 100 * 380 * pairs / (t * 1e-3) / peak))
+        t2 = graph_time(lambda: ops.match_cost_factors(x1, x2, fac), reps=2)
+        print("match_cost f+g   %8.2f us" % (t2 * 1e3))
+        print("EMD fwd+grad     %8.2f us  %5.1f%% of fp32 peak (423 flop/pair)" % ((t + t2) * 1e3, 100 * 423 * pairs / ((t + t2) * 1e-3) / peak))
+
+
+if __name__ == "__main__":
+    main()

@@ -12,11 +12,14 @@
 //  * the inner loop tracks minima only (FMNMX); indices are recovered afterwards
 //    from a coarse tag: the 32-column chunk in which a row's minimum first appeared,
 //    and the R-row group (one lane's rows) that produced a column's minimum;
-//  * a persistent sweep launch: warps pull (element, 32*R rows, kCols columns) tasks from
-//    an atomic queue; partial (min, tag) keys go to an L2-resident workspace with plain
-//    coalesced stores; a second, fully parallel launch (programmatic dependent launch)
-//    reduces the partials of every point and re-evaluates the <=32 (rows) / R (columns)
-//    tagged candidates to emit the exact first argmin.
+//  * sweep launch: the (element, 256-row block, 32-column chunk) units are split into
+//    equal contiguous spans, one per resident warp (stream-K style: no queue, no
+//    CTA barrier, balance to one unit); a warp keeps its rows in registers while it
+//    walks the chunks of a row block, the next chunk's columns arrive by cp.async;
+//    partial (min, tag) keys go to an L2-resident workspace with coalesced stores;
+//  * finalize launch (programmatic dependent launch): four lanes per output point
+//    reduce its partial keys and re-evaluate the <=32 (rows) / R (columns) tagged
+//    candidates with the same arithmetic to emit the exact first argmin.
 #include <cooperative_groups.h>
 
 #include "pnae_common.cuh"
@@ -28,13 +31,10 @@ namespace {
 typedef unsigned long long u64;
 
 constexpr int kR = 8;                 // rows per lane (contiguous: lane l owns rows l*kR .. l*kR+kR-1 of the block)
-constexpr int kRowsPerTask = 32 * kR; // 256
-#ifndef PNAE_NN_COLS
-#define PNAE_NN_COLS 64
-#endif
-constexpr int kCols = PNAE_NN_COLS;   // columns per task
-constexpr int kChunk = 32;            // columns per row-argmin tag
+constexpr int kRowsPerBlock = 32 * kR; // 256 rows per warp
+constexpr int kChunk = 32;            // columns per unit = columns per row-argmin tag
 constexpr int kWarps = 4;             // warps per CTA (independent; no CTA-wide barrier anywhere)
+constexpr int kGroup = 4;             // columns whose cross-lane reductions are batched
 #ifndef PNAE_NN_CTAS
 #define PNAE_NN_CTAS 4
 #endif
@@ -44,14 +44,22 @@ constexpr size_t kWsBudget = 256ull << 20;
 struct FwdParams {
     int be;            // elements in this launch
     int n, m;
-    int nrb, ncr;      // row blocks / column ranges per element
+    int nrb, nch;      // row blocks / column chunks per element
+    int nslot;         // row-partial slots per row block (max warps whose spans touch one row block)
+    long long units;   // be * nrb * nch
+    long long warps;   // sweep grid size in warps: the span of warp w is [w*units/warps, (w+1)*units/warps)
     const float *xyz1, *xyz2;
     float *dist1, *dist2;
     int *idx1, *idx2;
-    u64 *rowkeys;      // [be][ncr][n]  (min bits << 32 | global chunk index)
-    u64 *colkeys;      // [be][nrb][m]  (min bits << 32 | ballot of lanes holding the min)
-    int *ctr;          // [0] task queue head
+    u64 *rowkeys;      // [be][nrb][nslot][256]  (min bits << 32 | chunk index)
+    u64 *colkeys;      // [be][nrb][m]           (min bits << 32 | ballot of lanes holding the min)
 };
+
+// warp that owns unit u under the span formula above
+__device__ __forceinline__ long long owner_of(long long u, long long warps, long long units)
+{
+    return ((u + 1) * warps - 1) / units;
+}
 
 // cp.async (LDGSTS) helpers: 4-byte granularity because points are 12-byte xyz triples
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
@@ -61,128 +69,79 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Start the asynchronous copy of a main task's operands into this warp's staging buffers:
-// its 32*kR rows as flat xyz floats, its kCols columns as float4 slots (w unused).
-__device__ __forceinline__ void prefetch_task(const FwdParams &p, int e, int rb, int cr, float *srow, float4 *scol)
+// asynchronous copy of one chunk's 32 columns into float4 slots (w unused) and, on a row-block
+// change, of the block's 256 rows as flat xyz floats
+__device__ __forceinline__ void prefetch_unit(const FwdParams &p, int e, int rb, int ch, float *srow, float4 *scol,
+                                              bool with_rows)
 {
     const int lane = threadIdx.x & 31;
-    const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
     const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
-    const int row0 = rb * kRowsPerTask, col0 = cr * kCols;
+    const int col0 = ch * kChunk;
 #pragma unroll
-    for (int i = 0; i < kRowsPerTask * 3 / 32; i++) {
-        const int f = lane + 32 * i, r = f / 3;
-        const int j = min(row0 + r, p.n - 1);              // clamped duplicates never change a minimum
-        cp_async4(srow + f, p1 + (size_t)j * 3 + (f - r * 3));
-    }
-#pragma unroll
-    for (int i = 0; i < kCols * 3 / 32; i++) {
+    for (int i = 0; i < 3; i++) {
         const int f = lane + 32 * i, c = f / 3;
-        const int k = min(col0 + c, p.m - 1);
+        const int k = min(col0 + c, p.m - 1);              // clamped duplicates never change a minimum
         cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), p2 + (size_t)k * 3 + (f - c * 3));
+    }
+    if (with_rows) {
+        const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
+        const int row0 = rb * kRowsPerBlock;
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) {
+            const int f = lane + 32 * i, r = f / 3;
+            const int j = min(row0 + r, p.n - 1);
+            cp_async4(srow + f, p1 + (size_t)j * 3 + (f - r * 3));
+        }
     }
     cp_async_commit();
 }
 
-// Sweep one task: 32*kR rows (kR per lane, in registers) against kCols staged columns.
-// Leaves the partial keys in the workspace; completion is signalled later (see the kernel).
-__device__ __forceinline__ void main_task(const FwdParams &p, int e, int rb, int cr,
-                                          const float4 *scol, u64 *skey,
-                                          const float (&rx)[kR], const float (&ry)[kR], const float (&rz)[kR])
-{
-    const int lane = threadIdx.x & 31;
-    float best[kR], snap[kR];
-    int tag[kR];
-    const int row0 = rb * kRowsPerTask + lane * kR;
-#pragma unroll
-    for (int r = 0; r < kR; r++) {
-        best[r] = snap[r] = __int_as_float(0x7f800000);
-        tag[r] = 0;
-    }
-    const int col0 = cr * kCols;
-
-    for (int ch = 0; ch < kCols / kChunk; ch++) {
-#pragma unroll 4
-        for (int cc = 0; cc < kChunk; cc++) {
-            const int c = ch * kChunk + cc;
-            const float4 q = scol[c];
-            float d[kR];
-#pragma unroll
-            for (int r = 0; r < kR; r++) {
-                d[r] = pnae_sqdist(q.x - rx[r], q.y - ry[r], q.z - rz[r]);
-                best[r] = fminf(best[r], d[r]);
-            }
-            // column minimum over this lane's rows (tree), then over the warp
-#pragma unroll
-            for (int s = kR / 2; s > 0; s >>= 1)
-#pragma unroll
-                for (int r = 0; r < s; r++) d[r] = fminf(d[r], d[r + s]);
-            const unsigned bits = __float_as_uint(d[0]);      // d >= 0: unsigned order == float order
-            const unsigned mn = __reduce_min_sync(0xffffffffu, bits);
-            const unsigned who = __ballot_sync(0xffffffffu, bits == mn);
-            if (lane == 0) skey[c] = ((u64)mn << 32) | who;
-        }
-        // a strict decrease during this chunk => the row's running minimum first appears here
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-            if (best[r] < snap[r]) tag[r] = ch;
-            snap[r] = best[r];
-        }
-    }
-    __syncwarp();
-    // partial keys: [cr][row] and [rb][col], coalesced
-    u64 *rk = p.rowkeys + ((size_t)e * p.ncr + cr) * p.n;
-#pragma unroll
-    for (int r = 0; r < kR; r++) {
-        const int j = row0 + r;
-        if (j < p.n) rk[j] = ((u64)__float_as_uint(best[r]) << 32) | (unsigned)(cr * (kCols / kChunk) + tag[r]);
-    }
-    u64 *ck = p.colkeys + ((size_t)e * p.nrb + rb) * p.m;
-#pragma unroll
-    for (int c = lane; c < kCols; c += 32)
-        if (col0 + c < p.m) ck[col0 + c] = skey[c];
-}
-
-// One persistent launch for the sweep.  Each warp is an independent worker (no CTA-wide barrier
-// anywhere): tasks (element, row block, column range) come from one atomic queue, claimed TWO
-// ahead, so the atomic's round trip and the cp.async operand copy of the next task hide under
-// the current task's FP32 work.
+// Sweep launch.  Each warp is an independent worker walking its span of units.
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 nn_fwd_kernel(const FwdParams p)
 {
-    __shared__ __align__(16) float4 scol_all[kWarps][2][kCols];
-    __shared__ __align__(16) float srow_all[kWarps][kRowsPerTask * 3];
-    __shared__ u64 skey_all[kWarps][kCols];
+    __shared__ __align__(16) float4 scol_all[kWarps][2][kChunk];
+    __shared__ __align__(16) float srow_all[kWarps][kRowsPerBlock * 3];
+    __shared__ __align__(16) u64 skey_all[kWarps][kChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int main_per_e = p.nrb * p.ncr;
-    const long long n_main = (long long)p.be * main_per_e;
     float *srow = srow_all[warp];
+    const long long wid = (long long)blockIdx.x * kWarps + warp;
+    long long u = wid * p.units / p.warps;
+    const long long uend = (wid + 1) * p.units / p.warps;
+    if (u >= uend) return;
 
-    auto decode = [&](long long t, int &e, int &rb, int &cr) {
-        e = (int)(t / main_per_e);
-        const int r = (int)(t - (long long)e * main_per_e);
-        rb = r / p.ncr;          // column range fastest: neighbouring tasks share the row block
-        cr = r - rb * p.ncr;
+    const int per_e = p.nrb * p.nch;
+    auto decode = [&](long long t, int &e, int &rb, int &ch) {
+        e = (int)(t / per_e);
+        const int r = (int)(t - (long long)e * per_e);
+        rb = r / p.nch;          // chunk fastest: a span stays inside one row block as long as possible
+        ch = r - rb * p.nch;
     };
-    auto claim = [&]() -> unsigned { return lane == 0 ? atomicAdd((unsigned *)p.ctr, 1u) : 0u; };
-    auto bcast = [&](unsigned v) -> long long { return (long long)__shfl_sync(0xffffffffu, v, 0); };
 
-    long long cur = bcast(claim());
-    long long nxt = bcast(claim());
-    int buf = 0;
-    if (cur < n_main) {
-        int e, rb, cr;
-        decode(cur, e, rb, cr);
-        prefetch_task(p, e, rb, cr, srow, scol_all[warp][buf]);
-    }
-    while (cur < n_main) {
-        const unsigned pend = claim();            // task after next; consumed at the bottom of the loop
-        int e, rb, cr;
-        decode(cur, e, rb, cr);
+    float rx[kR], ry[kR], rz[kR], best[kR], snap[kR];
+    int tag[kR];
+    int e, rb, ch, held_e = -1, held_rb = -1, buf = 0;
+    long long held_u0 = 0;        // first unit this warp swept in the row block it holds
+    decode(u, e, rb, ch);
+    prefetch_unit(p, e, rb, ch, srow, scol_all[warp][buf], true);
+
+    // store this warp's partial row keys of the row block it is leaving
+    auto flush_rows = [&]() {
+        const long long first = ((long long)held_e * p.nrb + held_rb) * p.nch;      // first unit of the row block
+        // rank of this warp among the warps whose spans touch the row block: consecutive warps when every
+        // warp has work (units >= warps), one warp per unit otherwise -- the smaller of the two counts
+        const int slot = (int)min(wid - owner_of(first, p.warps, p.units), held_u0 - first);
+        u64 *rk = p.rowkeys + ((((size_t)held_e * p.nrb + held_rb) * p.nslot + slot) * kRowsPerBlock) + lane * kR;
+#pragma unroll
+        for (int r = 0; r < kR; r++) rk[r] = ((u64)__float_as_uint(best[r]) << 32) | (unsigned)tag[r];
+    };
+
+    for (; u < uend; u++) {
+        decode(u, e, rb, ch);
         cp_async_wait_all();
         __syncwarp();
-        float rx[kR], ry[kR], rz[kR];
-        {
+        if (e != held_e || rb != held_rb) {
+            if (held_e >= 0) flush_rows();
             const float4 *src = reinterpret_cast<const float4 *>(srow + lane * kR * 3);
             float tmp[kR * 3];
 #pragma unroll
@@ -191,52 +150,93 @@ nn_fwd_kernel(const FwdParams p)
                 tmp[4 * i] = v.x; tmp[4 * i + 1] = v.y; tmp[4 * i + 2] = v.z; tmp[4 * i + 3] = v.w;
             }
 #pragma unroll
-            for (int r = 0; r < kR; r++) { rx[r] = tmp[3 * r]; ry[r] = tmp[3 * r + 1]; rz[r] = tmp[3 * r + 2]; }
+            for (int r = 0; r < kR; r++) {
+                rx[r] = tmp[3 * r]; ry[r] = tmp[3 * r + 1]; rz[r] = tmp[3 * r + 2];
+                best[r] = snap[r] = __int_as_float(0x7f800000);
+                tag[r] = 0;
+            }
+            held_e = e; held_rb = rb; held_u0 = u;
         }
         __syncwarp();      // every lane has its rows in registers: the row buffer may be refilled
-        if (nxt < n_main) {
-            int e2, rb2, cr2;
-            decode(nxt, e2, rb2, cr2);
-            prefetch_task(p, e2, rb2, cr2, srow, scol_all[warp][buf ^ 1]);
+        if (u + 1 < uend) {
+            int e2, rb2, ch2;
+            decode(u + 1, e2, rb2, ch2);
+            prefetch_unit(p, e2, rb2, ch2, srow, scol_all[warp][buf ^ 1], e2 != e || rb2 != rb);
         }
-        main_task(p, e, rb, cr, scol_all[warp][buf], skey_all[warp], rx, ry, rz);
-        buf ^= 1;
+
+        // ---- 256 rows x 32 columns
+        const float4 *scol = scol_all[warp][buf];
+        u64 *skey = skey_all[warp];
+        float4 qn = scol[0];
+        for (int c0 = 0; c0 < kChunk; c0 += kGroup) {
+            // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
+            // independent chains, issued back to back so their fixed latencies overlap
+            unsigned bits[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; g++) {
+                const float4 q = qn;
+                qn = scol[(c0 + g + 1) & (kChunk - 1)];  // next column's record is in flight during this column's math
+                float d[kR];
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    d[r] = pnae_sqdist(q.x - rx[r], q.y - ry[r], q.z - rz[r]);
+                    best[r] = fminf(best[r], d[r]);
+                }
+                // column minimum over this lane's rows (tree); d >= 0: unsigned order == float order
+#pragma unroll
+                for (int s = kR / 2; s > 0; s >>= 1)
+#pragma unroll
+                    for (int r = 0; r < s; r++) d[r] = fminf(d[r], d[r + s]);
+                bits[g] = __float_as_uint(d[0]);
+            }
+            unsigned mn[kGroup], who[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; g++) mn[g] = __reduce_min_sync(0xffffffffu, bits[g]);
+#pragma unroll
+            for (int g = 0; g < kGroup; g++) who[g] = __ballot_sync(0xffffffffu, bits[g] == mn[g]);
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < kGroup; g += 2)
+                    *reinterpret_cast<ulonglong2 *>(skey + c0 + g) =
+                        make_ulonglong2(((u64)mn[g] << 32) | who[g], ((u64)mn[g + 1] << 32) | who[g + 1]);
+            }
+        }
         __syncwarp();
-        cur = nxt;
-        nxt = bcast(pend);
+        const u64 mykey = skey[lane];                    // lane c carries the key of column c of this chunk
+        __syncwarp();
+        // a strict decrease during this chunk => the row's running minimum first appears here
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            if (best[r] < snap[r]) tag[r] = ch;
+            snap[r] = best[r];
+        }
+        const int k = ch * kChunk + lane;
+        if (k < p.m) p.colkeys[((size_t)e * p.nrb + rb) * p.m + k] = mykey;
+        buf ^= 1;
     }
+    flush_rows();
 }
 
-// Second (tiny, fully parallel) launch: kFinLanes lanes per output point.  Each group reduces the
-// point's partial keys, then re-evaluates the tagged candidates (32 columns for a point of xyz1,
-// kR rows for a point of xyz2) with the same arithmetic as the sweep; the lowest index whose
-// distance equals the minimum is the reference's first argmin.  All loads of a phase are
-// independent, so a point costs three dependent L2 round trips.
+// Finalize launch: kFinLanes lanes per output point.  Each group reduces the point's partial
+// keys, then re-evaluates the tagged candidates (32 columns for a point of xyz1, kR rows for a
+// point of xyz2) with the same arithmetic as the sweep; the lowest index whose distance equals
+// the minimum is the reference's first argmin.  All loads of a phase are independent, so a
+// point costs two dependent L2 round trips.
 constexpr int kFinLanes = 4;
 constexpr int kFinThreads = 256;
 
-__device__ __forceinline__ u64 group_min_u64(u64 v)
-{
-#pragma unroll
-    for (int o = kFinLanes / 2; o > 0; o >>= 1) {
-        const u64 w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = min(v, w);
-    }
-    return v;
-}
-
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFinThreads, 4)
 nn_finalize_kernel(const FwdParams p)
 {
-#if __CUDA_ARCH__ >= 900
-    cudaGridDependencySynchronize();      // launched with programmatic stream serialization
-#endif
     const int sub = threadIdx.x & (kFinLanes - 1);
     const long long per_e = (long long)p.n + p.m;
     const long long total = (long long)p.be * per_e;
     constexpr int kPtsPerWarp = 32 / kFinLanes;
     const long long warp_id = ((long long)blockIdx.x * kFinThreads + threadIdx.x) >> 5;
     const long long n_warps = (long long)gridDim.x * kFinThreads >> 5;
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();      // launched with programmatic stream serialization
+#endif
     for (long long base = warp_id * kPtsPerWarp; base < total; base += n_warps * kPtsPerWarp) {   // warp-uniform trip count
         const long long pt = base + (threadIdx.x & 31) / kFinLanes;
         const bool live = pt < total;
@@ -248,27 +248,35 @@ nn_finalize_kernel(const FwdParams p)
         if (r < p.n) {
             // point j of xyz1 -> dist1 / idx1
             const int j = r;
-            const u64 *rk = p.rowkeys + (size_t)e * p.ncr * p.n + j;
-            u64 key = ~0ull;
-            for (int cr = sub; cr < p.ncr; cr += 4 * kFinLanes) {
-                u64 v[4];
+            const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
+            const int rb = j / kRowsPerBlock;
+            const long long first = ((long long)e * p.nrb + rb) * p.nch;
+            const int nsl = (int)min(owner_of(first + p.nch - 1, p.warps, p.units) - owner_of(first, p.warps, p.units) + 1,
+                                     (long long)p.nch);     // see flush_rows
+            const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
+            u64 key = ~0ull;       // (min bits, chunk): u64 order = lower distance, then lower chunk
+            for (int sl = sub; sl < nsl; sl += 8 * kFinLanes) {
+                u64 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = (cr + u * kFinLanes < p.ncr) ? __ldcg(rk + (size_t)(cr + u * kFinLanes) * p.n) : ~0ull;
+                for (int t = 0; t < 8; t++) v[t] = (sl + t * kFinLanes < nsl) ? __ldcg(rk + (size_t)(sl + t * kFinLanes) * kRowsPerBlock) : ~0ull;
 #pragma unroll
-                for (int u = 0; u < 4; u++) key = min(key, v[u]);
+                for (int t = 0; t < 8; t++) key = min(key, v[t]);
             }
-            key = group_min_u64(key);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(0xffffffffu, key, o));
             const float want = __uint_as_float((unsigned)(key >> 32));
             const int k0 = (int)(unsigned)key * kChunk;
-            const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
             constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
+            float cx[kPer], cy[kPer], cz[kPer];
+#pragma unroll
+            for (int c = 0; c < kPer; c++) {
+                const int k = min(k0 + sub * kPer + c, p.m - 1);
+                cx[c] = __ldg(p2 + k * 3); cy[c] = __ldg(p2 + k * 3 + 1); cz[c] = __ldg(p2 + k * 3 + 2);
+            }
             int found = 0x7fffffff;
 #pragma unroll
-            for (int c = kPer - 1; c >= 0; c--) {
-                const int k = min(k0 + sub * kPer + c, p.m - 1);
-                const float d = pnae_sqdist(__ldg(p2 + k * 3) - x, __ldg(p2 + k * 3 + 1) - y, __ldg(p2 + k * 3 + 2) - z);
-                if (d == want) found = k;
-            }
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(cx[c] - x, cy[c] - y, cz[c] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
 #pragma unroll
             for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
             if (live && sub == 0) {
@@ -278,24 +286,29 @@ nn_finalize_kernel(const FwdParams p)
         } else {
             // point k of xyz2 -> dist2 / idx2
             const int k = r - p.n;
+            const float x = __ldg(p2 + k * 3), y = __ldg(p2 + k * 3 + 1), z = __ldg(p2 + k * 3 + 2);
             const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
-            u64 key = ~0ull;       // (min bits, row block) first: the lowest row block wins ties
-            for (int rb = sub; rb < p.nrb; rb += 4 * kFinLanes) {
-                u64 v[4];
+            u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
+            unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
+            for (int rb = sub; rb < p.nrb; rb += 8 * kFinLanes) {
+                u64 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = (rb + u * kFinLanes < p.nrb) ? __ldcg(ck + (size_t)(rb + u * kFinLanes) * p.m) : ~0ull;
+                for (int t = 0; t < 8; t++) v[t] = (rb + t * kFinLanes < p.nrb) ? __ldcg(ck + (size_t)(rb + t * kFinLanes) * p.m) : ~0ull;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const u64 cand = (v[u] & 0xffffffff00000000ull) | (unsigned)(rb + u * kFinLanes);
-                    if (v[u] != ~0ull) key = min(key, cand);
+                for (int t = 0; t < 8; t++) {
+                    const u64 cand = (v[t] & 0xffffffff00000000ull) | (unsigned)(rb + t * kFinLanes);
+                    if (rb + t * kFinLanes < p.nrb && cand < key) { key = cand; who = (unsigned)v[t]; }
                 }
             }
-            key = group_min_u64(key);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) {
+                const u64 k2 = __shfl_xor_sync(0xffffffffu, key, o);
+                const unsigned w2 = __shfl_xor_sync(0xffffffffu, who, o);
+                if (k2 < key) { key = k2; who = w2; }
+            }
             const int rbw = (int)(unsigned)key;
-            const unsigned who = (unsigned)__ldcg(ck + (size_t)rbw * p.m);      // ballot of lanes that held the min
             const float want = __uint_as_float((unsigned)(key >> 32));
-            const int j0 = rbw * kRowsPerTask + (__ffs(who) - 1) * kR;
-            const float x = __ldg(p2 + k * 3), y = __ldg(p2 + k * 3 + 1), z = __ldg(p2 + k * 3 + 2);
+            const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
             constexpr int kPer = kR / kFinLanes;
             int found = 0x7fffffff;
 #pragma unroll
@@ -315,26 +328,28 @@ nn_finalize_kernel(const FwdParams p)
 }
 
 struct FwdPlan {
-    int nrb, ncr, be;
-    size_t row_bytes, col_bytes, ctr_bytes;   // per launch chunk of `be` elements
+    int nrb, nch, nslot, be;
+    long long warps;
+    size_t row_bytes, col_bytes;   // per launch chunk of `be` elements
     size_t total;
 };
 
-FwdPlan make_plan(int b, int n, int m)
+FwdPlan make_plan(int b, int n, int m, int sms)
 {
     FwdPlan pl;
-    pl.nrb = (n + kRowsPerTask - 1) / kRowsPerTask;
-    pl.ncr = (m + kCols - 1) / kCols;
-    const size_t per_e = sizeof(u64) * ((size_t)pl.ncr * n + (size_t)pl.nrb * m);
-    long long be = (long long)(kWsBudget / (per_e ? per_e : 1));
-    // keep the task / counter arithmetic inside 32 bits
-    const long long tasks_per_e = (long long)pl.nrb * pl.ncr;
-    be = min(be, (long long)(0x7ff00000 / tasks_per_e));   // queue head (+ one overshoot per warp) stays inside 31 bits
+    pl.nrb = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+    pl.nch = (m + kChunk - 1) / kChunk;
+    pl.warps = (long long)sms * kCtasPerSm * kWarps;
+    // a row block's nch units are touched by at most ceil(nch / floor(units/warps)) + 1 spans; bound it
+    // independently of `be` (units >= nrb*nch): spans are never shorter than floor(nrb*nch/warps)
+    const long long min_span = max(1ll, (long long)pl.nrb * pl.nch / pl.warps);
+    pl.nslot = (int)min((long long)pl.nch, (pl.nch + min_span - 1) / min_span + 1);
+    const size_t per_e = sizeof(u64) * ((size_t)pl.nrb * pl.nslot * kRowsPerBlock + (size_t)pl.nrb * m);
+    const long long be = (long long)(kWsBudget / (per_e ? per_e : 1));
     pl.be = (int)max(1ll, min((long long)b, be));
-    pl.row_bytes = sizeof(u64) * (size_t)pl.be * pl.ncr * n;
+    pl.row_bytes = sizeof(u64) * (size_t)pl.be * pl.nrb * pl.nslot * kRowsPerBlock;
     pl.col_bytes = sizeof(u64) * (size_t)pl.be * pl.nrb * m;
-    pl.ctr_bytes = 256;
-    pl.total = pl.row_bytes + pl.col_bytes + pl.ctr_bytes;
+    pl.total = pl.row_bytes + pl.col_bytes;
     return pl;
 }
 
@@ -393,7 +408,7 @@ nn_bwd_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *
 extern "C" size_t pnae_nn_distance_workspace_bytes(int b, int n, int m)
 {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return make_plan(b, n, m).total;
+    return make_plan(b, n, m, pnae_sm_count()).total;
 }
 
 extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
@@ -403,7 +418,8 @@ extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, cons
     PNAE_REQUIRE(b >= 0 && n >= 1 && m >= 1, "nn_distance: need b>=0, n>=1, m>=1 (got b=%d n=%d m=%d)", b, n, m);
     PNAE_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "nn_distance: NULL pointer");
     if (b == 0) return PNAE_OK;
-    const FwdPlan pl = make_plan(b, n, m);
+    const int sms = pnae_sm_count();
+    const FwdPlan pl = make_plan(b, n, m, sms);
     if (workspace == nullptr || workspace_bytes < pl.total) {
         pnae_set_error("nn_distance: workspace too small (%zu < %zu bytes)", workspace_bytes, pl.total);
         return PNAE_ERR_WORKSPACE;
@@ -411,25 +427,24 @@ extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, cons
     PNAE_REQUIRE(pnae_aligned(workspace, 8), "nn_distance: workspace must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
-    const int grid = pnae_sm_count() * kCtasPerSm;
     for (int e0 = 0; e0 < b; e0 += pl.be) {
         FwdParams p;
         p.be = min(pl.be, b - e0);
-        p.n = n; p.m = m; p.nrb = pl.nrb; p.ncr = pl.ncr;
+        p.n = n; p.m = m; p.nrb = pl.nrb; p.nch = pl.nch; p.nslot = pl.nslot;
+        p.units = (long long)p.be * pl.nrb * pl.nch;
+        p.warps = pl.warps;
         p.xyz1 = xyz1 + (size_t)e0 * n * 3; p.xyz2 = xyz2 + (size_t)e0 * m * 3;
         p.dist1 = dist1 + (size_t)e0 * n; p.idx1 = idx1 + (size_t)e0 * n;
         p.dist2 = dist2 + (size_t)e0 * m; p.idx2 = idx2 + (size_t)e0 * m;
         p.rowkeys = (u64 *)ws;
         p.colkeys = (u64 *)(ws + pl.row_bytes);
-        p.ctr = (int *)(ws + pl.row_bytes + pl.col_bytes);
-        PNAE_CUDA_OK(cudaMemsetAsync(p.ctr, 0, sizeof(int), st));
-        nn_fwd_kernel<<<grid, kWarps * 32, 0, st>>>(p);
+        nn_fwd_kernel<<<(unsigned)(pl.warps / kWarps), kWarps * 32, 0, st>>>(p);
         PNAE_CUDA_OK(cudaGetLastError());
         {
             const long long groups = (long long)p.be * ((long long)n + m);
             const long long want_blocks = (groups * kFinLanes + kFinThreads - 1) / kFinThreads;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)min(want_blocks, (long long)pnae_sm_count() * 8));
+            cfg.gridDim = dim3((unsigned)min(want_blocks, (long long)sms * 24));
             cfg.blockDim = dim3(kFinThreads);
             cfg.stream = st;
             cudaLaunchAttribute attr[1];

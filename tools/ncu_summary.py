@@ -8,9 +8,10 @@ import sys
 
 rep = sys.argv[1]
 nl = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + kidx]
 d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
 print("kernel:", d.get("Kernel Name", ("", ""))[1][:100])
 for k in ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -29,7 +30,7 @@ tot = sum(v for _, v in st) or 1
 print("stall samples (all):")
 for h, v in sorted(st, key=lambda x: -x[1])[:12]:
     print("  %-40s %7.0f  %5.1f%%" % (h.replace("smsp__pcsamp_warps_issue_stalled_", ""), v, 100 * v / tot))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", ":::%d" % (kidx + 1)] if kidx else ["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h2 = rows[1]; ix = {h: i for i, h in enumerate(h2)}
 data = [r for r in rows[2:] if len(r) == len(h2)]

@@ -1,19 +1,28 @@
 // approx_match.cu -- approximate EMD soft assignment for sm_100a.
 //
 // Replaces approxmatch / approxmatchLauncher (reference:
-// tf_ops/approxmatch/tf_approxmatch_g.cu:1-182).  Same schedule: 10 levels
-// j=7..-2, three sweeps per level (A: ratioL, B: ratioR/remainR, C: match/remainL),
-// fp32 accumulators, the same FMA contractions the reference compiles to.
+// tf_ops/approxmatch/tf_approxmatch_g.cu:1-182).  Same algorithm: 10 levels j=7..-2
+// (level=-4^j, 0 at the end), per level  A: ratioL = remainL / (1e-9 + sum_l E remainR),
+// B: sumr = remainR * sum_k E ratioL -> ratioR, remainR,  C: remainL -= sum_l E ratioL ratioR
+// with E = exp(level * |x1_k - x2_l|^2), fp32 throughout, the reference's FMA contractions.
 //
-// What is different from the reference kernel:
-//  * one thread-block CLUSTER per batch element instead of one CTA: dataset rows
-//    (sweeps A, C) and query columns (sweep B) are split over the CTAs of the
-//    cluster, which meet at a hardware cluster barrier between sweeps; only the
-//    n- or m-long state vectors cross CTAs (through L2);
-//  * the per-level factors ratioL_j / ratioR_j are the primary output; the dense
-//    (b,m,n) tensor is only touched when the caller asks for it;
-//  * 2^t on the SFU with flush-to-zero (see pnae_ex2), one multiply for
-//    level*log2e, R owned points per thread so one LDS.128 feeds R pairs.
+// B200 design (DESIGN.md "approx_match"):
+//  * ONE persistent cooperative launch; every sweep of every batch element is spread over
+//    all SMs (stream-K style contiguous spans of (element, own-block, streamed-chunk) tasks),
+//    with a grid barrier between dependent sweeps.  The reference runs one CTA per element.
+//  * sweep C of level j and sweep A of level j+1 own the same points and stream the same
+//    points, so they share one pass over the pairs (one distance, two exponentials);
+//    the last level (level 0 => E == 1) degenerates to O(n+m) sums and is done in closed
+//    form; sweep C of the last level only feeds the dense `match`, which is never formed.
+//    27 exponentials per pair instead of 30.
+//  * the per-point epilogues (the divisions / clamps that produce ratioL, ratioR, remainL,
+//    remainR) are evaluated on the fly while a task stages its streamed points, from the
+//    previous sweep's partial sums -- no extra pass, no extra barrier.
+//  * the inner loop is packed FP32 (FFMA2/FADD2/FMUL2: two own points per thread share every
+//    instruction) feeding MUFU.EX2; on B200 the packed form lets the SFU run concurrently
+//    with the FMA pipe (profiles/r1_microbench_b200.txt: 9.5 vs 14.1 cycles per pair).
+//  * the per-level factors ratioL_j / ratioR_j are the output; the dense (b,m,n) tensor is
+//    only materialised (match_cost.cu) when the caller asks for it.
 #include <cooperative_groups.h>
 
 #include "pnae_common.cuh"
@@ -23,143 +32,298 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTile = 1024;   // streamed points per shared-memory tile (float4: x,y,z,weight)
-constexpr int kR = 2;         // owned points per thread per pass
+constexpr int kOwn = 2 * kThreads;     // own points per task: one packed pair per thread
+constexpr int kTs = 128;               // streamed points per task
+constexpr int kCtasPerSm = 2;
+constexpr int kLevels = PNAE_NUM_LEVELS;
 
-enum SweepKind { kSweepA = 0, kSweepB = 1, kSweepC = 2 };
+struct EmdParams {
+    int b, n, m;
+    const float *xyz1, *xyz2;
+    float *factors;        // (b, 10, n+m)
+    float *remL, *remR;    // [2][b][n], [2][b][m]   remaining mass, double-buffered by level parity
+    float *ps0, *ps1;      // [2][b][nslot][maxnm]   partial sums, double-buffered by stage parity
+    int nslot, maxnm;
+    float multiL, multiR;
+};
 
-// Stream `ns` points (coordinates `sp`, weights `sw`) past the owned points
-// [lo,hi) of `op`; acc_r = sum over streamed points, in index order, of
-//   A,B: fma(E, w, acc)        C: fma(E*rl_r, w, acc)   [+ match RMW]
-// then apply the sweep's epilogue to each owned point.
-template <int KIND>
-__device__ __forceinline__ void sweep(float4 *tile, float scale,
-                                      const float *__restrict__ op, int lo, int hi,
-                                      const float *__restrict__ sp, const float *sw, int ns,
-                                      float *remainL, float *remainR, float *ratioL, float *ratioR,
-                                      float *match_i, int n)
+// geometry of one sweep: `own` points are owned (accumulated) by threads, `str` points stream past
+struct Geo {
+    int nown, nstr;        // points per element on either side
+    int nob, nch;          // own blocks / streamed chunks per element
+    long long tasks;       // b * nob * nch, chunk fastest
+};
+
+__device__ __forceinline__ Geo make_geo(int b, int nown, int nstr)
 {
-    for (int base = lo; base < hi; base += kThreads * kR) {
-        float ox[kR], oy[kR], oz[kR], acc[kR], rl[kR];
-        int own[kR];
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-            own[r] = base + r * kThreads + (int)threadIdx.x;
-            const int j = min(own[r], hi - 1);
-            ox[r] = __ldg(op + j * 3 + 0);
-            oy[r] = __ldg(op + j * 3 + 1);
-            oz[r] = __ldg(op + j * 3 + 2);
-            acc[r] = (KIND == kSweepA) ? 1e-9f : 0.0f;
-            rl[r] = (KIND == kSweepC) ? __ldcg(ratioL + j) : 0.0f;
-        }
-        for (int s0 = 0; s0 < ns; s0 += kTile) {
-            const int cnt = min(kTile, ns - s0);
-            __syncthreads();
-            for (int t = threadIdx.x; t < cnt; t += kThreads) {
-                const float *p = sp + (size_t)(s0 + t) * 3;
-                tile[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldcg(sw + s0 + t));
+    Geo g;
+    g.nown = nown; g.nstr = nstr;
+    g.nob = (nown + kOwn - 1) / kOwn;
+    g.nch = (nstr + kTs - 1) / kTs;
+    g.tasks = (long long)b * g.nob * g.nch;
+    return g;
+}
+
+// CTA that owns task t when `tasks` tasks are split into contiguous spans over `ctas` CTAs
+__device__ __forceinline__ long long owner_of(long long t, long long ctas, long long tasks)
+{
+    return ((t + 1) * ctas - 1) / tasks;
+}
+
+// number of partial-sum slots the sweep with geometry g left for own block (e, ob)
+__device__ __forceinline__ int slots_of(const Geo &g, int e, int ob, long long ctas)
+{
+    const long long first = ((long long)e * g.nob + ob) * g.nch;
+    return (int)min(owner_of(first + g.nch - 1, ctas, g.tasks) - owner_of(first, ctas, g.tasks) + 1, (long long)g.nch);
+}
+
+// sum, in slot order, of the partial sums a previous sweep left for own point `i` of element e
+__device__ __forceinline__ float gather(const float *ps, const EmdParams &p, const Geo &g, int e, int i, long long ctas,
+                                        float init)
+{
+    const int ns = slots_of(g, e, i / kOwn, ctas);
+    const float *q = ps + ((size_t)e * p.nslot) * p.maxnm + i;
+    float s = init;
+    for (int t = 0; t < ns; t++) s = __fadd_rn(s, __ldcg(q + (size_t)t * p.maxnm));
+    return s;
+}
+
+enum Kind { kA0 = 0, kB = 1, kCA = 2, kC = 3 };
+
+struct __align__(16) Rec {   // one streamed point, duplicated for the packed (two-own-points) math
+    float x0, x1, y0, y1;    // (x,x,y,y)
+    float z0, z1, w0, w1;    // (z,z,w,w)   w = the sweep's first weight
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// One sweep over all elements.  lev = level index (0..9).
+//   kA0 : own k, stream l, w = remainR_0 = multiR                     -> ps0 = suml_0 (without the 1e-9)
+//   kB  : own l, stream k, w = ratioL_lev[k]                          -> ps0 = sumr (before * remainR)
+//   kCA : own k, stream l, w = ratioR_lev[l], v = remainR_{lev+1}[l]  -> ps0 = sumc_lev, ps1 = suml_{lev+1}
+//   kC  : as kCA without the A half (last real level)                 -> ps0 = sumc_lev
+template <int KIND>
+__device__ void sweep(const EmdParams &p, int lev, int stage, Rec *tile, float2 *tilev)
+{
+    const long long ctas = gridDim.x;
+    const bool rowside = (KIND != kB);
+    const Geo g = make_geo(p.b, rowside ? p.n : p.m, rowside ? p.m : p.n);
+    const Geo gprev = make_geo(p.b, rowside ? p.m : p.n, rowside ? p.n : p.m);   // geometry of the previous sweep
+    const float *own_xyz = rowside ? p.xyz1 : p.xyz2;
+    const float *str_xyz = rowside ? p.xyz2 : p.xyz1;
+    const int par = stage & 1;
+    float *out0 = p.ps0 + (size_t)par * p.b * p.nslot * p.maxnm;
+    float *out1 = p.ps1 + (size_t)par * p.b * p.nslot * p.maxnm;
+    const float *in0 = p.ps0 + (size_t)(par ^ 1) * p.b * p.nslot * p.maxnm;
+    const float *in1 = p.ps1 + (size_t)(par ^ 1) * p.b * p.nslot * p.maxnm;
+    const float c0 = pnae_level_scale(lev), c1 = pnae_level_scale(lev + 1);
+    const float2 sc0 = f2(c0, c0), sc1 = f2(c1, c1);
+
+    long long t = (long long)blockIdx.x * g.tasks / ctas;
+    const long long tend = ((long long)blockIdx.x + 1) * g.tasks / ctas;
+    const int per_e = g.nob * g.nch;
+
+    int held_e = -1, held_ob = -1;
+    long long held_t0 = 0;
+    float2 nox = f2(0, 0), noy = f2(0, 0), noz = f2(0, 0), rl = f2(0, 0), acc0 = f2(0, 0), acc1 = f2(0, 0);
+    int own_i0 = 0, own_i1 = 0;
+
+    auto flush = [&]() {
+        const long long first = ((long long)held_e * g.nob + held_ob) * g.nch;
+        const int slot = (int)min((long long)blockIdx.x - owner_of(first, ctas, g.tasks), held_t0 - first);
+        const size_t base = ((size_t)held_e * p.nslot + slot) * p.maxnm;
+        if (own_i0 < g.nown) { out0[base + own_i0] = acc0.x; if (KIND == kCA) out1[base + own_i0] = acc1.x; }
+        if (own_i1 < g.nown) { out0[base + own_i1] = acc0.y; if (KIND == kCA) out1[base + own_i1] = acc1.y; }
+    };
+
+    for (; t < tend; t++) {
+        const int e = (int)(t / per_e);
+        const int r = (int)(t - (long long)e * per_e);
+        const int ob = r / g.nch, ch = r - ob * g.nch;
+        const float *oxyz = own_xyz + (size_t)e * g.nown * 3;
+        const float *sxyz = str_xyz + (size_t)e * g.nstr * 3;
+
+        if (e != held_e || ob != held_ob) {
+            if (held_e >= 0) flush();
+            held_e = e; held_ob = ob; held_t0 = t;
+            own_i0 = ob * kOwn + 2 * threadIdx.x; own_i1 = own_i0 + 1;
+            const int a = min(own_i0, g.nown - 1), c = min(own_i1, g.nown - 1);
+            nox = f2(-__ldg(oxyz + a * 3), -__ldg(oxyz + c * 3));
+            noy = f2(-__ldg(oxyz + a * 3 + 1), -__ldg(oxyz + c * 3 + 1));
+            noz = f2(-__ldg(oxyz + a * 3 + 2), -__ldg(oxyz + c * 3 + 2));
+            if (KIND == kCA || KIND == kC) {
+                // ratioL_lev[k] of the own points, written by the B sweep of this level
+                const float *fl = p.factors + ((size_t)e * kLevels + lev) * (p.n + p.m);
+                rl = f2(__ldcg(fl + a), __ldcg(fl + c));
             }
-            __syncthreads();
-#pragma unroll 4
-            for (int t = 0; t < cnt; t++) {
-                const float4 p = tile[t];
-#pragma unroll
-                for (int r = 0; r < kR; r++) {
-                    const float d = pnae_sqdist(p.x - ox[r], p.y - oy[r], p.z - oz[r]);
-                    float e = pnae_ex2(__fmul_rn(d, scale));
-                    if (KIND == kSweepC) {
-                        e = __fmul_rn(e, rl[r]);
-                        if (match_i != nullptr && own[r] < hi) {
-                            float *mp = match_i + (size_t)(s0 + t) * n + own[r];
-                            *mp = __fmaf_rn(e, p.w, *mp);
-                        }
-                    }
-                    acc[r] = __fmaf_rn(e, p.w, acc[r]);
+            acc0 = f2(0, 0); acc1 = f2(0, 0);
+        }
+
+        // ---- stage the streamed chunk; evaluate the previous sweep's epilogue for its points
+        __syncthreads();
+        const int s0 = ch * kTs;
+        for (int i = threadIdx.x; i < kTs; i += kThreads) {
+            const int s = s0 + i;
+            const bool valid = s < g.nstr;
+            const int sc = valid ? s : g.nstr - 1;
+            const float x = __ldg(sxyz + sc * 3), y = __ldg(sxyz + sc * 3 + 1), z = __ldg(sxyz + sc * 3 + 2);
+            float w = 0.f, v = 0.f;
+            const bool writer = valid && ob == 0;      // exactly one task per (element, streamed point) stores state
+            if (KIND == kA0) {
+                w = p.multiR;
+            } else if (KIND == kB) {
+                // streamed k: remainL_lev, then ratioL_lev = remainL_lev / (1e-9 + suml_lev)   (:58, :159)
+                float rem;
+                if (lev == 0) rem = p.multiL;
+                else {
+                    const float prev = __ldcg(p.remL + ((size_t)((lev - 1) & 1) * p.b + e) * p.n + sc);
+                    rem = fmaxf(0.f, __fsub_rn(prev, gather(in0, p, gprev, e, sc, ctas, 0.f)));
+                }
+                const float suml = gather(lev == 0 ? in0 : in1, p, gprev, e, sc, ctas, 1e-9f);
+                w = __fdiv_rn(rem, suml);
+                if (writer) {
+                    p.remL[((size_t)(lev & 1) * p.b + e) * p.n + s] = rem;
+                    p.factors[((size_t)e * kLevels + lev) * (p.n + p.m) + s] = w;
+                }
+            } else {
+                // streamed l: sweep B's epilogue (:102-106)
+                const float rem = lev == 0 ? p.multiR : __ldcg(p.remR + ((size_t)(lev & 1) * p.b + e) * p.m + sc);
+                const float sumr = __fmul_rn(gather(in0, p, gprev, e, sc, ctas, 0.f), rem);
+                const float cons = fminf(__fdiv_rn(rem, __fadd_rn(sumr, 1e-9f)), 1.0f);
+                w = __fmul_rn(cons, rem);                        // ratioR_lev
+                v = fmaxf(0.f, __fsub_rn(rem, sumr));            // remainR_{lev+1}
+                if (writer) {
+                    p.remR[((size_t)((lev + 1) & 1) * p.b + e) * p.m + s] = v;
+                    p.factors[((size_t)e * kLevels + lev) * (p.n + p.m) + p.n + s] = w;
                 }
             }
+            if (!valid) { w = 0.f; v = 0.f; }                   // padding contributes exactly nothing
+            Rec rec;
+            rec.x0 = rec.x1 = x; rec.y0 = rec.y1 = y; rec.z0 = rec.z1 = z; rec.w0 = rec.w1 = w;
+            tile[i] = rec;
+            if (KIND == kCA) tilev[i] = f2(v, v);
         }
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-            const int j = own[r];
-            if (j >= hi) continue;
-            if (KIND == kSweepA) {
-                ratioL[j] = __fdiv_rn(remainL[j], acc[r]);                       // :58
-            } else if (KIND == kSweepB) {
-                const float rr = remainR[j];
-                const float sumr = __fmul_rn(acc[r], rr);                        // :102
-                const float consumption = fminf(__fdiv_rn(rr, __fadd_rn(sumr, 1e-9f)), 1.0f);
-                ratioR[j] = __fmul_rn(consumption, rr);                          // :104
-                remainR[j] = fmaxf(0.0f, __fsub_rn(rr, sumr));                   // :105
-            } else {
-                remainL[j] = fmaxf(0.0f, __fsub_rn(remainL[j], acc[r]));         // :159
+        __syncthreads();
+
+        // ---- own pair x kTs streamed points, packed FP32
+#pragma unroll 4
+        for (int i = 0; i < kTs; i++) {
+            const float4 r0 = *reinterpret_cast<const float4 *>(&tile[i].x0);
+            const float4 r1 = *reinterpret_cast<const float4 *>(&tile[i].z0);
+            const float2 dx = __fadd2_rn(f2(r0.x, r0.y), nox);
+            const float2 dy = __fadd2_rn(f2(r0.z, r0.w), noy);
+            const float2 dz = __fadd2_rn(f2(r1.x, r1.y), noz);
+            const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+            const float2 u = __fmul2_rn(d, sc0);
+            float2 ex = f2(pnae_ex2(u.x), pnae_ex2(u.y));
+            if (KIND == kCA || KIND == kC) ex = __fmul2_rn(ex, rl);           // (E * rl) * rr   (:151)
+            acc0 = __ffma2_rn(ex, f2(r1.z, r1.w), acc0);
+            if (KIND == kCA) {
+                const float2 u1 = __fmul2_rn(d, sc1);
+                const float2 e1 = f2(pnae_ex2(u1.x), pnae_ex2(u1.y));
+                acc1 = __ffma2_rn(e1, tilev[i], acc1);                        // sweep A of the next level
             }
+        }
+    }
+    if (held_e >= 0) flush();
+}
+
+// Last level (level == 0 => E == 1 for every pair): the three sweeps collapse to sums over points.
+// One CTA per element.  Needs remainR_9 and ratioR_8 (written while sweep C of level 8 staged its
+// points) and sumc_8 (ps0 of the previous stage).
+__device__ void last_level(const EmdParams &p, int stage, float *red)
+{
+    const long long ctas = gridDim.x;
+    const Geo grow = make_geo(p.b, p.n, p.m);
+    const float *in0 = p.ps0 + (size_t)((stage & 1) ^ 1) * p.b * p.nslot * p.maxnm;
+    const int lev = kLevels - 1;
+    auto block_sum = [&](float v) -> float {
+        v = warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float s = 0.f;
+        for (int w = 0; w < kThreads / 32; w++) s += red[w];
+        return s;
+    };
+    for (int e = blockIdx.x; e < p.b; e += gridDim.x) {
+        const float *remR9 = p.remR + ((size_t)(lev & 1) * p.b + e) * p.m;
+        float *fac = p.factors + ((size_t)e * kLevels + lev) * (p.n + p.m);
+        float s = 0.f;
+        for (int l = threadIdx.x; l < p.m; l += kThreads) s += __ldcg(remR9 + l);
+        const float suml = __fadd_rn(1e-9f, block_sum(s));                 // 1e-9 + sum_l 1 * remainR[l]
+        s = 0.f;
+        for (int k = threadIdx.x; k < p.n; k += kThreads) {
+            const float prev = __ldcg(p.remL + ((size_t)((lev - 1) & 1) * p.b + e) * p.n + k);
+            const float rem = fmaxf(0.f, __fsub_rn(prev, gather(in0, p, grow, e, k, ctas, 0.f)));
+            const float rl = __fdiv_rn(rem, suml);
+            fac[k] = rl;
+            s += rl;
+        }
+        const float sumk = block_sum(s);                                   // sum_k 1 * ratioL[k]
+        for (int l = threadIdx.x; l < p.m; l += kThreads) {
+            const float rem = __ldcg(remR9 + l);
+            const float sumr = __fmul_rn(sumk, rem);
+            const float cons = fminf(__fdiv_rn(rem, __fadd_rn(sumr, 1e-9f)), 1.0f);
+            fac[p.n + l] = __fmul_rn(cons, rem);
         }
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
-approx_match_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                    float *__restrict__ factors, float *match, float *ws)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+approx_match_kernel(const EmdParams p)
 {
-    __shared__ float4 tile[kTile];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int cs = (int)cluster.num_blocks();
-    const int crank = (int)cluster.block_rank();
-    const int ncluster = gridDim.x / cs;
-    const int cid = blockIdx.x / cs;
-
-    // integer division, tf_approxmatch_g.cu:4-10
-    const float multiL = (n >= m) ? 1.0f : (float)(m / n);
-    const float multiR = (n >= m) ? (float)(n / m) : 1.0f;
-
-    const int nper = (n + cs - 1) / cs, mper = (m + cs - 1) / cs;
-    const int klo = min(n, crank * nper), khi = min(n, klo + nper);
-    const int llo = min(m, crank * mper), lhi = min(m, llo + mper);
-
-    for (int i = cid; i < b; i += ncluster) {
-        const float *p1 = xyz1 + (size_t)i * n * 3;
-        const float *p2 = xyz2 + (size_t)i * m * 3;
-        float *remainL = ws + (size_t)i * (n + m);
-        float *remainR = remainL + n;
-        float *match_i = match ? match + (size_t)i * n * m : nullptr;
-
-        for (int k = klo + threadIdx.x; k < khi; k += kThreads) remainL[k] = multiL;
-        for (int l = llo + threadIdx.x; l < lhi; l += kThreads) remainR[l] = multiR;
-        if (match_i) {
-            // this CTA zeroes the rows l of its column slice (contiguous (lhi-llo)*n floats)
-            float *z = match_i + (size_t)llo * n;
-            const size_t cnt = (size_t)(lhi - llo) * n;
-            for (size_t t = threadIdx.x; t < cnt; t += kThreads) z[t] = 0.0f;
-        }
+    __shared__ Rec tile[kTs];
+    __shared__ float2 tilev[kTs];
+    __shared__ float red[kThreads / 32];
+    cg::grid_group grid = cg::this_grid();
+    int stage = 0;
+    sweep<kA0>(p, 0, stage++, tile, tilev);
+    __threadfence();
+    grid.sync();
+    for (int lev = 0; lev < kLevels - 1; lev++) {
+        sweep<kB>(p, lev, stage++, tile, tilev);
         __threadfence();
-        cluster.sync();
-
-        for (int lev = 0; lev < PNAE_NUM_LEVELS; lev++) {
-            const float scale = pnae_level_scale(lev);
-            float *ratioL = factors + ((size_t)i * PNAE_NUM_LEVELS + lev) * (n + m);
-            float *ratioR = ratioL + n;
-            sweep<kSweepA>(tile, scale, p1, klo, khi, p2, remainR, m, remainL, remainR, ratioL, ratioR, nullptr, n);
-            __threadfence();
-            cluster.sync();
-            sweep<kSweepB>(tile, scale, p2, llo, lhi, p1, ratioL, n, remainL, remainR, ratioL, ratioR, nullptr, n);
-            __threadfence();
-            cluster.sync();
-            sweep<kSweepC>(tile, scale, p1, klo, khi, p2, ratioR, m, remainL, remainR, ratioL, ratioR, match_i, n);
-            // next sweep A reads remainR (written in B, already synchronised) and this
-            // CTA's own remainL; the match RMW of a thread only touches its own k.
-            __syncthreads();
-        }
+        grid.sync();
+        if (lev < kLevels - 2) sweep<kCA>(p, lev, stage++, tile, tilev);
+        else sweep<kC>(p, lev, stage++, tile, tilev);
         __threadfence();
-        cluster.sync();   // workspace of this cluster is reused by its next element
+        grid.sync();
     }
+    last_level(p, stage, red);
+}
+
+struct EmdPlan {
+    int grid, nslot, maxnm;
+    size_t rem_floats, ps_floats, total;
+};
+
+EmdPlan make_plan(int b, int n, int m, int sms)
+{
+    EmdPlan pl;
+    pl.grid = sms * kCtasPerSm;
+    pl.maxnm = n > m ? n : m;
+    auto slots = [&](int nown, int nstr) -> int {
+        const long long nob = (nown + kOwn - 1) / kOwn, nch = (nstr + kTs - 1) / kTs;
+        const long long span = max(1ll, (long long)b * nob * nch / pl.grid);
+        return (int)min(nch, (nch + span - 1) / span + 1);
+    };
+    pl.nslot = max(slots(n, m), slots(m, n));
+    pl.rem_floats = 2 * (size_t)b * ((size_t)n + m);
+    pl.ps_floats = 2 * (size_t)b * pl.nslot * pl.maxnm;
+    pl.total = sizeof(float) * (pl.rem_floats + 2 * pl.ps_floats);
+    return pl;
 }
 
 }  // namespace
 
+int pnae_match_from_factors_impl(int b, int n, int m, const float *xyz1, const float *xyz2,
+                                 const float *factors, float *match, cudaStream_t st);
+
 extern "C" size_t pnae_approx_match_workspace_bytes(int b, int n, int m)
 {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return sizeof(float) * (size_t)b * ((size_t)n + (size_t)m);
+    return make_plan(b, n, m, pnae_sm_count()).total;
 }
 
 extern "C" int pnae_approx_match(int b, int n, int m, const float *xyz1, const float *xyz2,
@@ -169,29 +333,26 @@ extern "C" int pnae_approx_match(int b, int n, int m, const float *xyz1, const f
     PNAE_REQUIRE(b >= 0 && n >= 1 && m >= 1, "approx_match: need b>=0, n>=1, m>=1 (got b=%d n=%d m=%d)", b, n, m);
     PNAE_REQUIRE(xyz1 && xyz2 && factors, "approx_match: NULL pointer (factors is required)");
     if (b == 0) return PNAE_OK;
-    const size_t need = pnae_approx_match_workspace_bytes(b, n, m);
-    if (workspace == nullptr || workspace_bytes < need) {
-        pnae_set_error("approx_match: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    const EmdPlan pl = make_plan(b, n, m, pnae_sm_count());
+    if (workspace == nullptr || workspace_bytes < pl.total) {
+        pnae_set_error("approx_match: workspace too small (%zu < %zu bytes)", workspace_bytes, pl.total);
         return PNAE_ERR_WORKSPACE;
     }
-    const int sms = pnae_sm_count();
-    int cs = 8;
-    while (cs > 1 && (long long)b * cs > 2ll * sms) cs >>= 1;
-    while (cs > 1 && (n + cs - 1) / cs < 32 && (m + cs - 1) / cs < 32) cs >>= 1;   // tiny clouds: fewer, fuller CTAs
-    const int nclusters = (int)min((long long)b, (long long)(4 * sms / cs > 0 ? 4 * sms / cs : 1));
-
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nclusters * cs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, approx_match_kernel, b, n, m, xyz1, xyz2, factors, match, (float *)workspace));
+    PNAE_REQUIRE(pnae_aligned(workspace, 4), "approx_match: workspace must be 4-byte aligned");
+    EmdParams p;
+    p.b = b; p.n = n; p.m = m;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.factors = factors;
+    float *ws = (float *)workspace;
+    p.remL = ws;
+    p.remR = ws + 2 * (size_t)b * n;
+    p.ps0 = ws + pl.rem_floats;
+    p.ps1 = p.ps0 + pl.ps_floats;
+    p.nslot = pl.nslot; p.maxnm = pl.maxnm;
+    p.multiL = (n >= m) ? 1.0f : (float)(m / n);      // integer division, tf_approxmatch_g.cu:4-10
+    p.multiR = (n >= m) ? (float)(n / m) : 1.0f;
+    cudaStream_t st = (cudaStream_t)stream;
+    void *args[] = {(void *)&p};
+    PNAE_CUDA_OK(cudaLaunchCooperativeKernel((const void *)approx_match_kernel, dim3(pl.grid), dim3(kThreads), args, 0, st));
+    if (match != nullptr) return pnae_match_from_factors_impl(b, n, m, xyz1, xyz2, factors, match, st);
     return PNAE_OK;
 }

@@ -286,6 +286,17 @@ extern "C" int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, c
     return PNAE_OK;
 }
 
+int pnae_match_from_factors_impl(int b, int n, int m, const float *xyz1, const float *xyz2,
+                                 const float *factors, float *match, cudaStream_t st)
+{
+    const int nkb = (n + kDThreads - 1) / kDThreads, nlb = (m + kDRows - 1) / kDRows;
+    const long long grid = (long long)b * nkb * nlb;
+    PNAE_REQUIRE(grid < (1ll << 31), "match_from_factors: problem too large for one launch");
+    match_from_factors_kernel<<<(unsigned)grid, kDThreads, 0, st>>>(n, m, xyz1, xyz2, factors, match, nkb, nlb);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}
+
 extern "C" int pnae_match_from_factors(int b, int n, int m, const float *xyz1, const float *xyz2,
                                        const float *factors, float *match, void *stream)
 {
@@ -293,12 +304,7 @@ extern "C" int pnae_match_from_factors(int b, int n, int m, const float *xyz1, c
     if (rc) return rc;
     PNAE_REQUIRE(factors && match, "match_from_factors: NULL pointer");
     if (b == 0) return PNAE_OK;
-    const int nkb = (n + kDThreads - 1) / kDThreads, nlb = (m + kDRows - 1) / kDRows;
-    const long long grid = (long long)b * nkb * nlb;
-    PNAE_REQUIRE(grid < (1ll << 31), "match_from_factors: problem too large for one launch");
-    match_from_factors_kernel<<<(unsigned)grid, kDThreads, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, factors, match, nkb, nlb);
-    PNAE_CUDA_OK(cudaGetLastError());
-    return PNAE_OK;
+    return pnae_match_from_factors_impl(b, n, m, xyz1, xyz2, factors, match, (cudaStream_t)stream);
 }
 
 extern "C" int pnae_match_cost_fwd(int b, int n, int m, const float *xyz1, const float *xyz2,

@@ -20,108 +20,132 @@ constexpr int kL = PNAE_NUM_LEVELS;
 // factor path
 // ---------------------------------------------------------------------------
 constexpr int kFThreads = 128;
-constexpr int kFR = 2;        // dataset rows per thread
-constexpr int kFTile = 128;   // query columns per shared-memory tile
+constexpr int kFRows = 2 * kFThreads;   // dataset rows per CTA: one packed pair per thread
+constexpr int kFTile = 64;              // query columns per shared-memory tile
 
-struct __align__(16) ColRec {   // one streamed query point: coordinates + its 10 ratioR_j
+struct __align__(16) ColRec {   // one streamed query point: coordinates + its 10 ratioR_j (dense-path kernels)
     float x, y, z, pad;
     float rr[12];
 };
 
+// the same, every value duplicated, so a thread's two rows share packed FP32 instructions
+struct __align__(16) ColRec2 {
+    float4 xy;        // x x y y
+    float4 zr0;       // z z rr0 rr0
+    float4 r12, r34, r56, r78;   // rr1 rr1 rr2 rr2 | ...
+    float4 r9;        // rr9 rr9 - -
+};
+
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+
+// cost[i] += sum sqrt(d) * match ; grad1 += ... ; grad2 += ...   for rows [rb*kFRows, +kFRows) x columns [l_lo, l_hi)
+// match[l,k] = sum_j (E_j * ratioL_j[k]) * ratioR_j[l], accumulated in level order like `match+=w` (:152).
+// sqrt(d) is formed as d * rsqrt(max(d,1e-20)) (one SFU op serves cost and gradient; <= 3 ulp per
+// term against the reference's IEEE sqrtf, far inside the 1e-5 on the summed cost).
 template <bool WITH_GRAD>
 __global__ void __launch_bounds__(kFThreads)
 match_cost_factors_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                           const float *__restrict__ factors, float *__restrict__ cost,
-                          float *__restrict__ grad1, float *__restrict__ grad2, int nblk)
+                          float *__restrict__ grad1, float *__restrict__ grad2, int nrb, int nsplit, int cols_per_split)
 {
-    __shared__ ColRec tile[kFTile];
+    __shared__ ColRec2 tile[kFTile];
+    __shared__ float g2s[kFThreads / 32][kFTile][3];
     __shared__ float red[kFThreads / 32];
 
-    const int i = blockIdx.x / nblk;
-    const int rb = blockIdx.x - i * nblk;
+    int bid = blockIdx.x;
+    const int sp = bid % nsplit; bid /= nsplit;
+    const int rb = bid % nrb;
+    const int i = bid / nrb;
     const float *p1 = xyz1 + (size_t)i * n * 3;
     const float *p2 = xyz2 + (size_t)i * m * 3;
     const float *fac = factors + (size_t)i * kL * (n + m);
+    const int l_lo = sp * cols_per_split, l_hi = min(m, l_lo + cols_per_split);
 
-    float x1[kFR], y1[kFR], z1[kFR], rl[kFR][kL];
-    float gx[kFR], gy[kFR], gz[kFR];
-    bool live[kFR];
-    int row[kFR];
-    float csum = 0.f;
+    const int k0 = rb * kFRows + 2 * (int)threadIdx.x, k1 = k0 + 1;
+    const bool live0 = k0 < n, live1 = k1 < n;
+    const int a = min(k0, n - 1), c = min(k1, n - 1);
+    const float2 x1 = mk2(__ldg(p1 + a * 3), __ldg(p1 + c * 3));
+    const float2 y1 = mk2(__ldg(p1 + a * 3 + 1), __ldg(p1 + c * 3 + 1));
+    const float2 z1 = mk2(__ldg(p1 + a * 3 + 2), __ldg(p1 + c * 3 + 2));
+    float2 rl[kL];
 #pragma unroll
-    for (int r = 0; r < kFR; r++) {
-        row[r] = rb * (kFThreads * kFR) + r * kFThreads + (int)threadIdx.x;
-        live[r] = row[r] < n;
-        const int k = min(row[r], n - 1);
-        x1[r] = __ldg(p1 + k * 3); y1[r] = __ldg(p1 + k * 3 + 1); z1[r] = __ldg(p1 + k * 3 + 2);
-#pragma unroll
-        for (int j = 0; j < kL; j++) rl[r][j] = live[r] ? __ldg(fac + (size_t)j * (n + m) + k) : 0.f;
-        gx[r] = gy[r] = gz[r] = 0.f;
-    }
+    for (int j = 0; j < kL; j++)      // dead rows carry zero weight: they contribute exactly nothing
+        rl[j] = mk2(live0 ? __ldg(fac + (size_t)j * (n + m) + a) : 0.f, live1 ? __ldg(fac + (size_t)j * (n + m) + c) : 0.f);
+    float2 gx = mk2(0, 0), gy = mk2(0, 0), gz = mk2(0, 0), csum = mk2(0, 0);
 
-    const int lane = threadIdx.x & 31;
-    for (int l0 = 0; l0 < m; l0 += kFTile) {
-        const int cnt = min(kFTile, m - l0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int l0 = l_lo; l0 < l_hi; l0 += kFTile) {
+        const int cnt = min(kFTile, l_hi - l0);
         __syncthreads();
         for (int t = threadIdx.x; t < cnt; t += kFThreads) {
             const int l = l0 + t;
-            ColRec c;
-            c.x = __ldg(p2 + l * 3); c.y = __ldg(p2 + l * 3 + 1); c.z = __ldg(p2 + l * 3 + 2); c.pad = 0.f;
+            const float x = __ldg(p2 + l * 3), y = __ldg(p2 + l * 3 + 1), z = __ldg(p2 + l * 3 + 2);
+            float r[kL];
 #pragma unroll
-            for (int j = 0; j < kL; j++) c.rr[j] = __ldg(fac + (size_t)j * (n + m) + n + l);
-            c.rr[10] = c.rr[11] = 0.f;
-            tile[t] = c;
+            for (int j = 0; j < kL; j++) r[j] = __ldg(fac + (size_t)j * (n + m) + n + l);
+            ColRec2 rec;
+            rec.xy = make_float4(x, x, y, y);
+            rec.zr0 = make_float4(z, z, r[0], r[0]);
+            rec.r12 = make_float4(r[1], r[1], r[2], r[2]);
+            rec.r34 = make_float4(r[3], r[3], r[4], r[4]);
+            rec.r56 = make_float4(r[5], r[5], r[6], r[6]);
+            rec.r78 = make_float4(r[7], r[7], r[8], r[8]);
+            rec.r9 = make_float4(r[9], r[9], 0.f, 0.f);
+            tile[t] = rec;
         }
         __syncthreads();
         for (int t = 0; t < cnt; t++) {
-            const float4 p = *reinterpret_cast<const float4 *>(&tile[t].x);
-            const float4 ra = *reinterpret_cast<const float4 *>(&tile[t].rr[0]);
-            const float4 rb4 = *reinterpret_cast<const float4 *>(&tile[t].rr[4]);
-            const float4 rc = *reinterpret_cast<const float4 *>(&tile[t].rr[8]);
-            const float rr[kL] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z, rb4.w, rc.x, rc.y};
-            float g2x = 0.f, g2y = 0.f, g2z = 0.f;
+            const float4 xy = tile[t].xy, zr0 = tile[t].zr0, r12 = tile[t].r12, r34 = tile[t].r34;
+            const float4 r56 = tile[t].r56, r78 = tile[t].r78, r9 = tile[t].r9;
+            const float2 rr[kL] = {mk2(zr0.z, zr0.w), mk2(r12.x, r12.y), mk2(r12.z, r12.w), mk2(r34.x, r34.y), mk2(r34.z, r34.w),
+                                   mk2(r56.x, r56.y), mk2(r56.z, r56.w), mk2(r78.x, r78.y), mk2(r78.z, r78.w), mk2(r9.x, r9.y)};
+            // x1 - x2 (grad1 direction, :281); the square is symmetric
+            const float2 dx = __fadd2_rn(x1, mk2(-xy.x, -xy.y));
+            const float2 dy = __fadd2_rn(y1, mk2(-xy.z, -xy.w));
+            const float2 dz = __fadd2_rn(z1, mk2(-zr0.x, -zr0.y));
+            const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+            float2 mv = mk2(0, 0);
 #pragma unroll
-            for (int r = 0; r < kFR; r++) {
-                const float dx = x1[r] - p.x, dy = y1[r] - p.y, dz = z1[r] - p.z;
-                const float d = pnae_sqdist(dx, dy, dz);
-                float mv = 0.f;    // match[l,k], accumulated in level order like `match+=w` (:152)
-#pragma unroll
-                for (int j = 0; j < kL; j++) {
-                    const float e = pnae_ex2(__fmul_rn(d, pnae_level_scale(j)));
-                    mv = __fmaf_rn(__fmul_rn(e, rl[r][j]), rr[j], mv);
-                }
-                csum = __fmaf_rn(__fsqrt_rn(d), mv, csum);                      // :207-208
-                if (WITH_GRAD) {
-                    const float w = __fmul_rn(mv, pnae_rsqrt(fmaxf(d, 1e-20f)));   // :243, :281
-                    gx[r] = __fmaf_rn(dx, w, gx[r]); gy[r] = __fmaf_rn(dy, w, gy[r]); gz[r] = __fmaf_rn(dz, w, gz[r]);
-                    g2x = __fmaf_rn(-dx, w, g2x); g2y = __fmaf_rn(-dy, w, g2y); g2z = __fmaf_rn(-dz, w, g2z);
-                }
+            for (int j = 0; j < kL - 1; j++) {
+                const float cj = pnae_level_scale(j);
+                const float2 u = __fmul2_rn(d, mk2(cj, cj));
+                const float2 e = mk2(pnae_ex2(u.x), pnae_ex2(u.y));
+                mv = __ffma2_rn(__fmul2_rn(e, rl[j]), rr[j], mv);
             }
+            mv = __ffma2_rn(rl[kL - 1], rr[kL - 1], mv);                  // last level: E == 1
+            const float2 rs = mk2(pnae_rsqrt(fmaxf(d.x, 1e-20f)), pnae_rsqrt(fmaxf(d.y, 1e-20f)));   // :243, :281
+            csum = __ffma2_rn(__fmul2_rn(d, rs), mv, csum);               // sqrt(d) * match   (:207-208)
             if (WITH_GRAD) {
-                g2x = warp_sum(g2x); g2y = warp_sum(g2y); g2z = warp_sum(g2z);
-                if (lane == 0) {
-                    float *g = grad2 + ((size_t)i * m + l0 + t) * 3;
-                    atomicAdd(g, g2x); atomicAdd(g + 1, g2y); atomicAdd(g + 2, g2z);
-                }
+                const float2 w = __fmul2_rn(mv, rs);
+                gx = __ffma2_rn(dx, w, gx); gy = __ffma2_rn(dy, w, gy); gz = __ffma2_rn(dz, w, gz);
+                const float2 tx = __fmul2_rn(dx, w), ty = __fmul2_rn(dy, w), tz = __fmul2_rn(dz, w);
+                const float sx = warp_sum(tx.x + tx.y), sy = warp_sum(ty.x + ty.y), sz = warp_sum(tz.x + tz.y);
+                if (lane == 0) { g2s[warp][t][0] = -sx; g2s[warp][t][1] = -sy; g2s[warp][t][2] = -sz; }
+            }
+        }
+        if (WITH_GRAD) {
+            __syncthreads();
+            for (int q = threadIdx.x; q < cnt * 3; q += kFThreads) {
+                const int t = q / 3, ax = q - t * 3;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < kFThreads / 32; w++) v += g2s[w][t][ax];
+                atomicAdd(grad2 + ((size_t)i * m + l0 + t) * 3 + ax, v);
             }
         }
     }
     if (WITH_GRAD) {
-#pragma unroll
-        for (int r = 0; r < kFR; r++)
-            if (live[r]) {
-                float *g = grad1 + ((size_t)i * n + row[r]) * 3;
-                g[0] = gx[r]; g[1] = gy[r]; g[2] = gz[r];
-            }
+        if (live0) { float *g = grad1 + ((size_t)i * n + k0) * 3; atomicAdd(g, gx.x); atomicAdd(g + 1, gy.x); atomicAdd(g + 2, gz.x); }
+        if (live1) { float *g = grad1 + ((size_t)i * n + k1) * 3; atomicAdd(g, gx.y); atomicAdd(g + 1, gy.y); atomicAdd(g + 2, gz.y); }
     }
-    csum = warp_sum(csum);
-    if (lane == 0) red[threadIdx.x >> 5] = csum;
+    float cs = warp_sum(csum.x + csum.y);
+    if (lane == 0) red[warp] = cs;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float s = 0.f;
+        float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kFThreads / 32; w++) s += red[w];
-        atomicAdd(cost + i, s);
+        for (int w = 0; w < kFThreads / 32; w++) v += red[w];
+        atomicAdd(cost + i, v);
     }
 }
 
@@ -274,13 +298,22 @@ extern "C" int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, c
     PNAE_REQUIRE((grad1 == nullptr) == (grad2 == nullptr), "match_cost_factors: pass both gradients or neither");
     if (b == 0) return PNAE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (n + kFThreads * kFR - 1) / (kFThreads * kFR);
+    const int nrb = (n + kFRows - 1) / kFRows;
+    // split the columns so that about seven CTAs land on every SM (all resident at once)
+    const int tiles = (m + kFTile - 1) / kFTile;
+    long long want = (7ll * pnae_sm_count() + (long long)b * nrb - 1) / ((long long)b * nrb);
+    const int nsplit = (int)max(1ll, min((long long)tiles, want));
+    const int cols_per_split = ((tiles + nsplit - 1) / nsplit) * kFTile;
+    const int nsp = (m + cols_per_split - 1) / cols_per_split;
+    const long long grid = (long long)b * nrb * nsp;
+    PNAE_REQUIRE(grid < (1ll << 31), "match_cost_factors: problem too large for one launch");
     PNAE_CUDA_OK(cudaMemsetAsync(cost, 0, sizeof(float) * (size_t)b, st));
     if (grad1) {
+        PNAE_CUDA_OK(cudaMemsetAsync(grad1, 0, sizeof(float) * (size_t)b * n * 3, st));
         PNAE_CUDA_OK(cudaMemsetAsync(grad2, 0, sizeof(float) * (size_t)b * m * 3, st));
-        match_cost_factors_kernel<true><<<(unsigned)(b * nblk), kFThreads, 0, st>>>(n, m, xyz1, xyz2, factors, cost, grad1, grad2, nblk);
+        match_cost_factors_kernel<true><<<(unsigned)grid, kFThreads, 0, st>>>(n, m, xyz1, xyz2, factors, cost, grad1, grad2, nrb, nsp, cols_per_split);
     } else {
-        match_cost_factors_kernel<false><<<(unsigned)(b * nblk), kFThreads, 0, st>>>(n, m, xyz1, xyz2, factors, cost, nullptr, nullptr, nblk);
+        match_cost_factors_kernel<false><<<(unsigned)grid, kFThreads, 0, st>>>(n, m, xyz1, xyz2, factors, cost, nullptr, nullptr, nrb, nsp, cols_per_split);
     }
     PNAE_CUDA_OK(cudaGetLastError());
     return PNAE_OK;

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .graphs import ChamferStep
 
 
 def _pinned(shape, dtype):
@@ -32,6 +33,8 @@ class ChamferHostRunner:
         self.d_xyz2 = torch.empty((b, m, 3), dtype=torch.float32, device=self.device)
         self.g1 = torch.full((b, n), 100.0 / (b * n), device=self.device)
         self.g2 = torch.full((b, m), 100.0 / (b * m), device=self.device)
+        with torch.cuda.device(self.device):
+            self.graph_step = ChamferStep(self.d_xyz1, self.d_xyz2, self.g1, self.g2)   # one launch per step
         self.h_out = {
             "dist1": _pinned((b, n), torch.float32), "idx1": _pinned((b, n), torch.int32),
             "dist2": _pinned((b, m), torch.float32), "idx2": _pinned((b, m), torch.int32),
@@ -53,10 +56,12 @@ class ChamferHostRunner:
         with torch.cuda.device(self.device):
             self.d_xyz1.copy_(self._stage(xyz1, self.h_xyz1), non_blocking=True)
             self.d_xyz2.copy_(self._stage(xyz2, self.h_xyz2), non_blocking=True)
-            g1 = self.g1 if grad_dist1 is None else torch.as_tensor(grad_dist1, dtype=torch.float32).to(self.device)
-            g2 = self.g2 if grad_dist2 is None else torch.as_tensor(grad_dist2, dtype=torch.float32).to(self.device)
-            d1, i1, d2, i2 = ops.nn_distance_fwd(self.d_xyz1, self.d_xyz2)
-            o1, o2 = ops.nn_distance_bwd(self.d_xyz1, self.d_xyz2, g1, i1, g2, i2)
+            if grad_dist1 is not None:
+                self.g1.copy_(torch.as_tensor(grad_dist1, dtype=torch.float32), non_blocking=True)
+            if grad_dist2 is not None:
+                self.g2.copy_(torch.as_tensor(grad_dist2, dtype=torch.float32), non_blocking=True)
+            st = self.graph_step.run()
+            d1, i1, d2, i2, o1, o2 = st.dist1, st.idx1, st.dist2, st.idx2, st.grad_xyz1, st.grad_xyz2
             for k, t in (("dist1", d1), ("idx1", i1), ("dist2", d2), ("idx2", i2), ("grad_xyz1", o1), ("grad_xyz2", o2)):
                 self.h_out[k].copy_(t, non_blocking=True)
             torch.cuda.current_stream().synchronize()

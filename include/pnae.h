@@ -110,6 +110,23 @@ PNAE_API int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, con
                             const float *factors, float *cost, float *grad1, float *grad2,
                             void *stream);
 
+/* ---- PointNet encoder: conv5 (1x1 conv = per-point linear map) + max-pool, fused ---------- */
+
+/* Replaces, for the encoder's dominant layer, the TF graph segment of get_model
+ * (models/model.py:57-66: tf_util.conv2d 128->1024 [utils/tf_util.py:155-185] followed by
+ * tf_util.max_pool2d over the points [:368-391]).
+ *   x_bf16  : (b, n, k)  bf16, the previous layer's activations (k = 64 or 128)
+ *   wt_bf16 : (c, k)     bf16, the layer's weight TRANSPOSED (reference layout is [1,1,k,c]); c % 128 == 0
+ * For y[i,p,ch] = sum_k x[i,p,k] * w[k,ch]  (fp32 accumulation on tcgen05 tensor cores, no bias) it writes,
+ * per batch element i and channel ch, over the n points p:
+ *   out_max, out_min, out_sum, out_sumsq : (b, c) float32 each.
+ * The (b, n, c) activation is never written.  Bias, BatchNorm (batch statistics come from sum/sumsq,
+ * folded inference statistics work the same way), ReLU and the max-pool then finish on (b, c):
+ *   pooled = relu(s*(ext + bias) + t),  ext = out_max where the BN scale s >= 0, out_min where s < 0. */
+PNAE_API int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
+                                    float *out_max, float *out_min, float *out_sum, float *out_sumsq,
+                                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

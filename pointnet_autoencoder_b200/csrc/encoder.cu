@@ -1,0 +1,289 @@
+// encoder.cu -- the PointNet encoder's dominant layer + pooling as ONE tensor-core kernel (sm_100a).
+//
+// Reference path: get_model, models/model.py:57-66 -- conv5 (1x1 conv 128 -> 1024, i.e. a per-point
+// linear map: utils/tf_util.py:155-185) -> bias -> BatchNorm -> ReLU -> max over the points
+// (tf_util.max_pool2d, :368-391).  89% of the encoder's FLOPs are this one GEMM, and the reference
+// writes and re-reads the (B, N, 1024) activation (268 MB at B=32) three or more times.
+//
+// Here:  D[channel, point] = W5^T[channel, :] . X[point, :]   (bf16 operands, fp32 accumulate)
+//  * tcgen05.mma (UMMA 128 x 256 x 16, cta_group::1), operands staged by TMA into 128B-swizzled
+//    shared memory, accumulators double-buffered in TMEM (2 x 256 columns);
+//  * channels are the M (TMEM lane) dimension, so each epilogue thread owns one channel and the
+//    reduction over points is a private register reduction straight out of tcgen05.ld:
+//    running max, min, sum and sum of squares per (batch element, channel);
+//  * the activation never leaves the SM.  max and min are kept because
+//    max_n relu(s*y_n + t) = relu(s*max_n y_n + t) for s >= 0 and relu(s*min_n y_n + t) for s < 0
+//    (s, t = folded BatchNorm scale/shift), and sum / sum^2 are exactly the batch statistics
+//    training-mode BatchNorm needs -- so BN (either mode) + ReLU + max-pool finish on a (B,1024)
+//    tensor ("Training-mode BatchNorm blocks naive encoder fusion").
+//  * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation),
+//    warps 2..5 = epilogue (one TMEM lane quadrant each); mbarrier pipelines smem<->MMA<->epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "pnae_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;        // channels per CTA (UMMA M)
+constexpr int kTileN = 256;        // points per MMA tile (UMMA N)
+constexpr int kKBox = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int kMaxK = 128;
+constexpr int kStages = 2;
+constexpr int kEncThreads = 192;   // 6 warps
+constexpr int kSpinLimit = 1 << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a descriptor mistake must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)=2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// grid = (C/128) x B.  Each CTA: 128 channels of one batch element, looping over its point tiles.
+__global__ void __launch_bounds__(kEncThreads, 1)
+encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                         int n, int k, int c, float *__restrict__ omax, float *__restrict__ omin,
+                         float *__restrict__ osum, float *__restrict__ osq)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int kboxes = k / kKBox;
+    const uint32_t a_bytes = (uint32_t)kboxes * kTileM * 128;           // W block
+    const uint32_t b_bytes = (uint32_t)kboxes * kTileN * 128;           // one X stage
+    uint8_t *sa = smem;
+    uint8_t *sb = smem + a_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sb + kStages * b_bytes);
+    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + kStages;
+    uint64_t *t_full = b_empty + kStages, *t_empty = t_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cb = blockIdx.x, e = blockIdx.y;
+    const int ntiles = (n + kTileN - 1) / kTileN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+        mbar_init(a_full, 1);
+        for (int s = 0; s < kStages; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(a_full, a_bytes);
+            for (int kb = 0; kb < kboxes; kb++) tma_load_2d(sa + (size_t)kb * kTileM * 128, &tm_w, kb * kKBox, cb * kTileM, a_full);
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t % kStages;
+                if (t >= kStages) mbar_wait(b_empty + s, ((t / kStages) - 1) & 1);
+                mbar_expect_tx(b_full + s, b_bytes);
+                for (int kb = 0; kb < kboxes; kb++)
+                    tma_load_2d(sb + (size_t)s * b_bytes + (size_t)kb * kTileN * 128, &tm_x, kb * kKBox, e * n + t * kTileN, b_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTileM, kTileN);
+            mbar_wait(a_full, 0);
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t % kStages, buf = t & 1;
+                if (t >= 2) mbar_wait(t_empty + buf, ((t >> 1) - 1) & 1);      // epilogue drained this accumulator
+                mbar_wait(b_full + s, (t / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kk = 0; kk < k / 16; kk++) {
+                    const int kb = kk >> 2, kin = kk & 3;                      // 4 UMMA_K=16 steps per 128-byte row
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sa + (size_t)kb * kTileM * 128) + kin * 32);
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sb + (size_t)s * b_bytes + (size_t)kb * kTileN * 128) + kin * 32);
+                    umma_bf16(tmem_base + buf * kTileN, ad, bd, idesc, kk > 0);
+                }
+                umma_commit(b_empty + s);       // smem stage reusable once these MMAs retire
+                umma_commit(t_full + buf);      // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: one thread per channel, reduction over points in registers =====
+        const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+        float vmax = -__int_as_float(0x7f800000), vmin = __int_as_float(0x7f800000), vsum = 0.f, vsq = 0.f;
+        for (int t = 0; t < ntiles; t++) {
+            const int buf = t & 1;
+            const int valid = min(kTileN, n - t * kTileN);
+            mbar_wait(t_full + buf, (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN;
+#pragma unroll 1
+            for (int ch = 0; ch < kTileN / 32; ch++) {
+                float v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                if ((ch + 1) * 32 <= valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
+                        vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (ch * 32 + i < valid) {
+                            vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
+                            vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
+                        }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(t_empty + buf);
+        }
+        const int ch_out = cb * kTileM + q * 32 + lane;
+        if (ch_out < c) {
+            const size_t o = (size_t)e * c + ch_out;
+            omax[o] = vmax; omin[o] = vmin; osum[o] = vsum; osq[o] = vsq;
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rows x k bf16, row-major (k contiguous): box = 64 elements (128 B) x box_rows, 128B swizzle
+int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t k, uint32_t box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { pnae_set_error("cuTensorMapEncodeTiled is not available from this driver"); return PNAE_ERR_CUDA; }
+    cuuint64_t dims[2] = {k, rows};
+    cuuint64_t strides[1] = {k * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {(cuuint32_t)kKBox, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pnae_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PNAE_ERR_CUDA; }
+    return PNAE_OK;
+}
+
+}  // namespace
+
+extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
+                                      float *out_max, float *out_min, float *out_sum, float *out_sumsq, void *stream)
+{
+    PNAE_REQUIRE(b >= 0 && n >= 1, "encoder_conv_pool: need b>=0, n>=1 (got b=%d n=%d)", b, n);
+    PNAE_REQUIRE(k >= kKBox && k <= kMaxK && k % kKBox == 0, "encoder_conv_pool: in-channels must be 64 or 128 (got %d)", k);
+    PNAE_REQUIRE(c >= kTileM && c % kTileM == 0, "encoder_conv_pool: out-channels must be a multiple of 128 (got %d)", c);
+    PNAE_REQUIRE(x_bf16 && wt_bf16 && out_max && out_min && out_sum && out_sumsq, "encoder_conv_pool: NULL pointer");
+    PNAE_REQUIRE(pnae_aligned(x_bf16, 16) && pnae_aligned(wt_bf16, 16), "encoder_conv_pool: operands must be 16-byte aligned");
+    if (b == 0) return PNAE_OK;
+    CUtensorMap tm_w, tm_x;
+    int rc = make_map(&tm_w, wt_bf16, (uint64_t)c, (uint64_t)k, kTileM);
+    if (rc) return rc;
+    rc = make_map(&tm_x, x_bf16, (uint64_t)b * n, (uint64_t)k, kTileN);
+    if (rc) return rc;
+    const int kboxes = k / kKBox;
+    const size_t smem = 1024 + (size_t)kboxes * kTileM * 128 + (size_t)kStages * kboxes * kTileN * 128 + 256;
+    PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(c / kTileM), (unsigned)b);
+    encoder_conv_pool_kernel<<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}

@@ -183,3 +183,24 @@ def match_cost_factors(xyz1, xyz2, factors, with_grad=True):
         g2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev) if with_grad else None
         _lib.check(lib.pnae_match_cost_factors(b, n, m, _p(xyz1), _p(xyz2), _p(factors), _p(cost), _p(g1), _p(g2), _stream(xyz1)))
     return (cost, g1, g2) if with_grad else cost
+
+
+# ---------------------------------------------------------------------------
+# encoder: conv5 + max-pool (models/model.py:57-66)
+# ---------------------------------------------------------------------------
+def encoder_conv_pool(x_bf16, wt_bf16):
+    """x (B,N,K) bf16, wt (C,K) bf16 -> max, min, sum, sumsq of x @ wt.T over the points, each (B,C) fp32"""
+    _dev(x_bf16, "x"); _dev(wt_bf16, "wt")
+    _require(x_bf16.dim() == 3 and wt_bf16.dim() == 2 and x_bf16.shape[2] == wt_bf16.shape[1],
+             "encoder_conv_pool expects x (batch,#points,k) and wt (c,k)")
+    if x_bf16.dtype != torch.bfloat16 or wt_bf16.dtype != torch.bfloat16:
+        raise TypeError("encoder_conv_pool expects bfloat16 operands")
+    x = x_bf16.contiguous(); wt = wt_bf16.contiguous()
+    b, n, k = x.shape
+    c = wt.shape[0]
+    lib = _lib.load()
+    dev = x.device
+    with torch.cuda.device(dev):
+        outs = [torch.empty((b, c), dtype=torch.float32, device=dev) for _ in range(4)]
+        _lib.check(lib.pnae_encoder_conv_pool(b, n, k, c, _p(x), _p(wt), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _stream(x)))
+    return tuple(outs)

@@ -57,5 +57,32 @@ def main():
         print("EMD fwd+grad     %8.2f us  %5.1f%% of fp32 peak (423 flop/pair)" % ((t + t2) * 1e3, 100 * 423 * pairs / ((t + t2) * 1e-3) / peak))
 
 
+def enc():
+    b, n, k, c = 32, 2048, 128, 1024
+    x = torch.randn(b, n, k, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(k, c, device="cuda") / k ** 0.5)
+    wt = w.t().contiguous().to(torch.bfloat16)
+    t = graph_time(lambda: ops.encoder_conv_pool(x, wt), reps=10)
+    flop = 2.0 * b * n * k * c
+    print("encoder conv5+pool (tcgen05)   %8.2f us  %7.1f TFLOP/s  (%.1f%% of the 1660.6 TF/s measured bf16 burst peak)" % (t * 1e3, flop / (t * 1e-3) / 1e12, 100 * flop / (t * 1e-3) / 1660.6e12))
+    xf = x.float()
+
+    def lib():
+        y = torch.relu(xf @ w)
+        return y.amax(1)
+    t2 = graph_time(lib, reps=5)
+    print("torch fp32 matmul+relu+amax    %8.2f us" % (t2 * 1e3))
+    xb = x; wb = w.to(torch.bfloat16)
+
+    def lib16():
+        y = xb @ wb
+        return y.amax(1), y.amin(1), y.float().sum(1)
+    t3 = graph_time(lib16, reps=5)
+    print("torch bf16 matmul+amax/amin/sum %7.2f us" % (t3 * 1e3))
+
+
 if __name__ == "__main__":
+    if "--enc" in sys.argv:
+        enc()
+        sys.exit(0)
     main()

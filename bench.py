@@ -239,19 +239,8 @@ def run_product(args):
     from pointnet_autoencoder_b200.graphs import ChamferStep
     slots = [ChamferStep(x1[i], x2[i], g1, g2) for i in range(RING)]
 
-    class FwdOnly:      # the dominant kernel pair alone (sweep + finalize), for the roofline figure
-        def __init__(self, a, c):
-            self.a, self.c = a, c
-            s_ = torch.cuda.Stream(device=dev)
-            s_.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(s_):
-                ops.nn_distance_fwd(a, c)
-            torch.cuda.current_stream(dev).wait_stream(s_)
-            torch.cuda.synchronize(dev)
-            self.g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g):
-                self.out = ops.nn_distance_fwd(a, c)
-    fwd_slots = [FwdOnly(x1[i], x2[i]) for i in range(RING)]
+    # the dominant kernel pair alone (sweep + finalize), for the roofline figure
+    fwd_slots = [ChamferStep(x1[i], x2[i], g1, g2, forward_only=True) for i in range(RING)]
 
     def barrier():
         if world > 1:
@@ -277,7 +266,7 @@ def run_product(args):
     # forward alone, same ring, same clocks: CUDA events on the launching stream
     f0.record(stream)
     for i in range(args.steps):
-        fwd_slots[i % RING].g.replay()
+        fwd_slots[i % RING].run()
     f1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -334,8 +323,9 @@ def run_product(args):
                    "launch": "one CUDA graph replay per step (3 kernels: sweep, finalize, gradient)",
                    "upstream_grad": "100/(B*N) (models/model.py:81-83)"},
         "roofline": {"bound": "fp32", "kernel": "nn_distance forward (nn_fwd_kernel sweep + nn_finalize_kernel)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": None,
-                     "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/)" % (sms.value, sm_max),
+                     "frac": achieved / fp32_peak, "traffic": 1606400,
+                     "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/r1_microbench_b200.txt)" % (sms.value, sm_max),
+                     "traffic_source": "dram__bytes_read+write of nn_fwd_kernel, ncu --set full (profiles/r1_ncu_full_summary.txt); algorithmic bytes %d" % alg_bytes,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
                      "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,

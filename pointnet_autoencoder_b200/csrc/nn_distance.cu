@@ -485,3 +485,70 @@ extern "C" int pnae_nn_distance_bwd(int b, int n, const float *xyz1, int m, cons
                                     grad_xyz1, grad_xyz2));
     return PNAE_OK;
 }
+
+// ---------------------------------------------------------------------------
+// CUDA-graph form of one Chamfer step (forward + gradient): the three kernels are captured once
+// over fixed buffers and replayed with a single launch.  At B=32, N=M=2048 the step is ~80 us of
+// GPU time, less than launching it kernel by kernel costs on the host.
+// ---------------------------------------------------------------------------
+struct PnaeGraph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+};
+
+extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                         float *dist1, int *idx1, float *dist2, int *idx2,
+                                         const float *grad_dist1, const float *grad_dist2,
+                                         float *grad_xyz1, float *grad_xyz2,
+                                         void *workspace, size_t workspace_bytes, void **handle)
+{
+    PNAE_REQUIRE(handle != nullptr, "chamfer_graph_create: NULL handle");
+    *handle = nullptr;
+    cudaStream_t st;
+    PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    int rc = PNAE_OK;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) {
+        cudaStreamDestroy(st);
+        pnae_set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    rc = pnae_nn_distance_fwd(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, st);
+    if (rc == PNAE_OK && grad_xyz1 != nullptr && grad_xyz2 != nullptr)     // NULL gradients: forward only
+        rc = pnae_nn_distance_bwd(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, st);
+    ce = cudaStreamEndCapture(st, &graph);
+    cudaStreamDestroy(st);
+    if (rc != PNAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || graph == nullptr) {
+        pnae_set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        pnae_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    PnaeGraph *g = new PnaeGraph{graph, exec};
+    *handle = g;
+    return PNAE_OK;
+}
+
+extern "C" int pnae_graph_launch(void *handle, void *stream)
+{
+    PNAE_REQUIRE(handle != nullptr, "graph_launch: NULL handle");
+    PNAE_CUDA_OK(cudaGraphLaunch(static_cast<PnaeGraph *>(handle)->exec, (cudaStream_t)stream));
+    return PNAE_OK;
+}
+
+extern "C" int pnae_graph_destroy(void *handle)
+{
+    if (handle == nullptr) return PNAE_OK;
+    PnaeGraph *g = static_cast<PnaeGraph *>(handle);
+    cudaGraphExecDestroy(g->exec);
+    cudaGraphDestroy(g->graph);
+    delete g;
+    return PNAE_OK;
+}

@@ -2,16 +2,18 @@
 
 At B=32, N=M=2048 the forward + gradient is three kernels and about 80 us of GPU time;
 launching them from Python one call at a time costs more host time than that.  A
-`ChamferStep` fixes the buffers (inputs, outputs, workspace) once, captures
-NnDistance + NnDistanceGrad through the C ABI into one CUDA graph and replays it with a
-single launch per step.  Results are identical to the eager calls (same kernels, same
+`ChamferStep` fixes the buffers (inputs, outputs, workspace) once, has the C library capture
+NnDistance + NnDistanceGrad into one CUDA graph (pnae_chamfer_graph_create) and replays it
+with a single launch per step.  Results are identical to the eager calls (same kernels, same
 arguments).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
-from . import ops
+from . import _lib
 
 
 class ChamferStep:
@@ -20,34 +22,45 @@ class ChamferStep:
     After `run()` the results are in .dist1 .idx1 .dist2 .idx2 .grad_xyz1 .grad_xyz2 (static
     tensors, overwritten by every run).  To feed new data, copy into `.xyz1` / `.xyz2`."""
 
-    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None):
-        assert xyz1.is_cuda and xyz2.is_cuda
+    kernels_per_run = 3     # sweep, finalize, gradient
+
+    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False):
+        assert xyz1.is_cuda and xyz2.is_cuda and xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32
         self.xyz1 = xyz1.contiguous()
         self.xyz2 = xyz2.contiguous()
         b, n, _ = self.xyz1.shape
         m = self.xyz2.shape[1]
         dev = self.xyz1.device
-        self.g1 = grad_dist1 if grad_dist1 is not None else torch.full((b, n), 100.0 / (b * n), device=dev)
-        self.g2 = grad_dist2 if grad_dist2 is not None else torch.full((b, m), 100.0 / (b * m), device=dev)
-        self.graph = None
-        # warm-up on a side stream (required before capture), then capture
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(s):
-            self._eager()
-        torch.cuda.current_stream(dev).wait_stream(s)
-        torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._eager()
-        self.graph = g
-
-    def _eager(self):
-        self.dist1, self.idx1, self.dist2, self.idx2 = ops.nn_distance_fwd(self.xyz1, self.xyz2)
-        self.grad_xyz1, self.grad_xyz2 = ops.nn_distance_bwd(self.xyz1, self.xyz2, self.g1, self.idx1, self.g2, self.idx2)
+        self.device = dev
+        f32 = dict(dtype=torch.float32, device=dev); i32 = dict(dtype=torch.int32, device=dev)
+        self.g1 = grad_dist1 if grad_dist1 is not None else torch.full((b, n), 100.0 / (b * n), **f32)
+        self.g2 = grad_dist2 if grad_dist2 is not None else torch.full((b, m), 100.0 / (b * m), **f32)
+        self.dist1 = torch.empty((b, n), **f32); self.idx1 = torch.empty((b, n), **i32)
+        self.dist2 = torch.empty((b, m), **f32); self.idx2 = torch.empty((b, m), **i32)
+        self.grad_xyz1 = torch.empty((b, n, 3), **f32); self.grad_xyz2 = torch.empty((b, m, 3), **f32)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
+            self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize(dev)
+            h = C.c_void_p()
+            p = lambda t: C.c_void_p(t.data_ptr())
+            _lib.check(lib.pnae_chamfer_graph_create(b, n, p(self.xyz1), m, p(self.xyz2), p(self.dist1), p(self.idx1),
+                                                     p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),
+                                                     None if forward_only else p(self.grad_xyz1),
+                                                     None if forward_only else p(self.grad_xyz2), p(self.ws), wsb, C.byref(h)))
+        self._h = h
+        self._lib = lib
 
     def run(self):
-        self.graph.replay()
+        _lib.check(self._lib.pnae_graph_launch(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return self
 
-    kernels_per_run = 3     # sweep, finalize, gradient
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.pnae_graph_destroy(h)
+            except Exception:
+                pass
+            self._h = None

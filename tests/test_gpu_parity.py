@@ -79,6 +79,26 @@ def test_nn_distance_grad_vs_oracle(gen, b, n, m):
     np.testing.assert_allclose(x2.grad.cpu().numpy(), o2, rtol=1e-4, atol=1e-5)
 
 
+def test_chamfer_graph_step_equals_eager_calls():
+    from pointnet_autoencoder_b200.graphs import ChamferStep
+    xyz1, xyz2 = clouds("chair", 3, 700, 900)
+    x1 = cu(xyz1); x2 = cu(xyz2)
+    step = ChamferStep(x1, x2)
+    for _ in range(2):            # replaying must be idempotent
+        step.run()
+    torch.cuda.synchronize()
+    d1, i1, d2, i2 = ops.nn_distance_fwd(x1, x2)
+    g1, g2 = ops.nn_distance_bwd(x1, x2, step.g1, i1, step.g2, i2)
+    assert torch.equal(step.dist1, d1) and torch.equal(step.idx1, i1)
+    assert torch.equal(step.dist2, d2) and torch.equal(step.idx2, i2)
+    assert torch.allclose(step.grad_xyz1, g1, rtol=1e-5, atol=1e-9) and torch.allclose(step.grad_xyz2, g2, rtol=1e-5, atol=1e-9)
+    # new data through the same graph
+    other = x1.flip(0).contiguous()        # step.xyz1 aliases x1: take the new data before overwriting it
+    step.xyz1.copy_(other)
+    step.run(); torch.cuda.synchronize()
+    assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
+
+
 def test_nn_distance_chamfer_loss_grad_constant():
     # models/model.py:81-83: loss = 100*mean(dist1+dist2) -> upstream grad 100/(B*N)
     label, pred = synthetic.s_chair(2, 1024)

@@ -1,4 +1,4 @@
-"""Run each hot op a few times at the headline size (for ncu: -k regex:<kernel> -s 2 -c 1)."""
+"""Run each hot op a few times at the headline size (for ncu: -k regex:<kernel> -s <skip> -c <count>)."""
 import os
 import sys
 
@@ -12,12 +12,16 @@ b, n, m = 32, 2048, 2048
 x1n, x2n = synthetic.s_randn(b, n, m)
 x1 = torch.from_numpy(x1n).cuda(); x2 = torch.from_numpy(x2n).cuda()
 g1 = torch.full((b, n), 100.0 / (b * n), device="cuda"); g2 = torch.full((b, m), 100.0 / (b * m), device="cuda")
-for _ in range(4):
-    if which == "chamfer":
+xe = torch.randn(b, n, 128, device="cuda").to(torch.bfloat16)
+we = (torch.randn(1024, 128, device="cuda") / 128 ** 0.5).to(torch.bfloat16)
+for _ in range(3):
+    if which in ("chamfer", "all"):
         d1, i1, d2, i2 = ops.nn_distance_fwd(x1, x2)
         ops.nn_distance_bwd(x1, x2, g1, i1, g2, i2)
-    else:
+    if which in ("emd", "all"):
         fac = ops.approx_match_factors(x1, x2)
         ops.match_cost_factors(x1, x2, fac)
+    if which in ("enc", "all"):
+        ops.encoder_conv_pool(xe, we)
 torch.cuda.synchronize()
 print("ok")

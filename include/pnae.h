@@ -134,10 +134,13 @@ PNAE_API int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, con
  *   out_max, out_min, out_sum, out_sumsq : (b, c) float32 each.
  * The (b, n, c) activation is never written.  Bias, BatchNorm (batch statistics come from sum/sumsq,
  * folded inference statistics work the same way), ReLU and the max-pool then finish on (b, c):
- *   pooled = relu(s*(ext + bias) + t),  ext = out_max where the BN scale s >= 0, out_min where s < 0. */
+ *   pooled = relu(s*(ext + bias) + t),  ext = out_max where the BN scale s >= 0, out_min where s < 0.
+ * Optional (both or neither): sign (c,) float32 and out_arg (b, c) int32 -- out_arg[i,ch] is the index of the
+ * first point attaining the maximum (sign[ch] >= 0) or the minimum (sign[ch] < 0) of channel ch; the
+ * training backward routes the pooled gradient to that point. */
 PNAE_API int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
                                     float *out_max, float *out_min, float *out_sum, float *out_sumsq,
-                                    void *stream);
+                                    const float *sign, int *out_arg, void *stream);
 
 #ifdef __cplusplus
 }

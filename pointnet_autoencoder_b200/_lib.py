@@ -41,7 +41,7 @@ SIGNATURES = {
     "pnae_match_cost_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pnae_match_cost_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnae_match_cost_factors": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "pnae_encoder_conv_pool": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnae_encoder_conv_pool": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -113,10 +113,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 }
 
 // grid = (C/128) x B.  Each CTA: 128 channels of one batch element, looping over its point tiles.
+// ARG: also report, per (element, channel), the index of the first point attaining the extremum
+// the max-pool will select (the maximum where sign[channel] >= 0, the minimum otherwise): the
+// training backward needs it (the pooled gradient flows to that point only).
+template <bool ARG>
 __global__ void __launch_bounds__(kEncThreads, 1)
 encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                          int n, int k, int c, float *__restrict__ omax, float *__restrict__ omin,
-                         float *__restrict__ osum, float *__restrict__ osq)
+                         float *__restrict__ osum, float *__restrict__ osq,
+                         const float *__restrict__ sign, int *__restrict__ oarg)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -188,6 +193,11 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         // ===== epilogue: one thread per channel, reduction over points in registers =====
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
         float vmax = -__int_as_float(0x7f800000), vmin = __int_as_float(0x7f800000), vsum = 0.f, vsq = 0.f;
+        const int ch_mine = cb * kTileM + q * 32 + lane;
+        // key = +v (track the maximum) or -v (track the minimum): flipping the sign bit is exact
+        const unsigned flip = (ARG && ch_mine < c && sign[ch_mine] < 0.f) ? 0x80000000u : 0u;
+        float kbest = -__int_as_float(0x7f800000);
+        int ibest = 0;
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const int valid = min(kTileN, n - t * kTileN);
@@ -203,6 +213,10 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
                     for (int i = 0; i < 32; i++) {
                         vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
                         vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
+                        if (ARG) {
+                            const float key = __uint_as_float(__float_as_uint(v[i]) ^ flip);
+                            if (key > kbest) { kbest = key; ibest = t * kTileN + ch * 32 + i; }   // strict: first point wins
+                        }
                     }
                 } else {
 #pragma unroll
@@ -210,6 +224,10 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
                         if (ch * 32 + i < valid) {
                             vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
                             vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
+                            if (ARG) {
+                                const float key = __uint_as_float(__float_as_uint(v[i]) ^ flip);
+                                if (key > kbest) { kbest = key; ibest = t * kTileN + ch * 32 + i; }
+                            }
                         }
                 }
             }
@@ -220,6 +238,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         if (ch_out < c) {
             const size_t o = (size_t)e * c + ch_out;
             omax[o] = vmax; omin[o] = vmin; osum[o] = vsum; osq[o] = vsq;
+            if (ARG) oarg[o] = ibest;
         }
     }
 
@@ -266,8 +285,10 @@ int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t k, uint
 }  // namespace
 
 extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
-                                      float *out_max, float *out_min, float *out_sum, float *out_sumsq, void *stream)
+                                      float *out_max, float *out_min, float *out_sum, float *out_sumsq,
+                                      const float *sign, int *out_arg, void *stream)
 {
+    PNAE_REQUIRE((sign == nullptr) == (out_arg == nullptr), "encoder_conv_pool: pass both `sign` and `out_arg` or neither");
     PNAE_REQUIRE(b >= 0 && n >= 1, "encoder_conv_pool: need b>=0, n>=1 (got b=%d n=%d)", b, n);
     PNAE_REQUIRE(k >= kKBox && k <= kMaxK && k % kKBox == 0, "encoder_conv_pool: in-channels must be 64 or 128 (got %d)", k);
     PNAE_REQUIRE(c >= kTileM && c % kTileM == 0, "encoder_conv_pool: out-channels must be a multiple of 128 (got %d)", c);
@@ -281,9 +302,14 @@ extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_
     if (rc) return rc;
     const int kboxes = k / kKBox;
     const size_t smem = 1024 + (size_t)kboxes * kTileM * 128 + (size_t)kStages * kboxes * kTileN * 128 + 256;
-    PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c / kTileM), (unsigned)b);
-    encoder_conv_pool_kernel<<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq);
+    if (out_arg) {
+        PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encoder_conv_pool_kernel<true><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, sign, out_arg);
+    } else {
+        PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encoder_conv_pool_kernel<false><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, nullptr, nullptr);
+    }
     PNAE_CUDA_OK(cudaGetLastError());
     return PNAE_OK;
 }

@@ -29,50 +29,77 @@ BN_EPS = 1e-3
 
 
 class _Conv5Pool(torch.autograd.Function):
-    """pooled = max_n relu(BN(x @ w + bias)) with the forward on tensor cores; the backward
-    re-evaluates the layer with library GEMMs (only the arg-max points carry gradient through the
-    pool, but training-mode BN couples all points through its statistics)."""
+    """pooled = max_n relu(BN(x @ w + bias)), forward on tensor cores (csrc/encoder.cu), never forming
+    the (B, N, C) activation -- in the backward either.
+
+    Backward.  Only the arg-extremum point n*(b,c) receives the pooled gradient, but training-mode BN
+    couples all points through its statistics:
+        dy[b,n,c] = s_c * ( dz[b,n,c] - dbeta_c/T - xhat[b,n,c] * dgamma_c/T ),   T = B*N,
+        dz[b,n,c] = g[b,c] * [z* > 0] * delta(n, n*(b,c)).
+    With y0 = x @ w this is  dy = S + a_c + q_c * y0  (S sparse: one entry per (b,c)), hence
+        dW = gather(x, n*)^T (s g~) + sum_n x (x) a + (X^T X) w diag(q)        (a K x K Gram matrix)
+        dX = x (w diag(q) w^T) + w a + scatter(s g~ w^T at n*)                 (a K x K matrix)
+    i.e. two GEMMs with inner/outer size K=128 instead of three with C=1024, plus gathers on (B,C)."""
 
     @staticmethod
     def forward(ctx, x, w, bias, gamma, beta, run_mean, run_var, training, decay):
         b, n, k = x.shape
-        c = w.shape[1]
-        vmax, vmin, vsum, vsq = ops.encoder_conv_pool(x.to(torch.bfloat16), w.t().contiguous().to(torch.bfloat16))
+        xb = x.detach().to(torch.bfloat16)
+        wtb = w.detach().t().contiguous().to(torch.bfloat16)
+        need_arg = any(ctx.needs_input_grad[:5])
+        if need_arg:
+            vmax, vmin, vsum, vsq, arg = ops.encoder_conv_pool(xb, wtb, sign=gamma.detach())
+        else:
+            vmax, vmin, vsum, vsq = ops.encoder_conv_pool(xb, wtb)
+            arg = None
+        cnt = float(b * n)
         if training:
-            cnt = float(b * n)
-            mean_acc = vsum.sum(0) / cnt                       # of the GEMM output without bias
-            var = (vsq.sum(0) / cnt - mean_acc * mean_acc).clamp_min(0.0)
-            mean = mean_acc + bias
+            mean0 = vsum.sum(0) / cnt                          # of y0 = x @ w (no bias)
+            var = (vsq.sum(0) / cnt - mean0 * mean0).clamp_min(0.0)
             with torch.no_grad():
-                run_mean.mul_(decay).add_(mean, alpha=1.0 - decay)
+                run_mean.mul_(decay).add_(mean0 + bias, alpha=1.0 - decay)
                 run_var.mul_(decay).add_(var, alpha=1.0 - decay)
         else:
-            mean, var = run_mean, run_var
-        s = gamma * torch.rsqrt(var + BN_EPS)
-        t = beta - mean * s
-        ext = torch.where(s >= 0, vmax, vmin) + bias
-        pooled = F.relu(ext * s + t)
-        ctx.save_for_backward(x, w, bias, gamma, beta, run_mean, run_var)
+            mean0, var = run_mean - bias, run_var
+        inv = torch.rsqrt(var + BN_EPS)
+        s = gamma * inv
+        ext0 = torch.where(gamma >= 0, vmax, vmin)             # the extremum the pool selects, of y0
+        z = (ext0 - mean0) * s + beta
+        pooled = F.relu(z)
+        if need_arg:
+            ctx.save_for_backward(x, w, bias, gamma, inv, mean0, ext0, arg, z)
         ctx.training = training
+        ctx.cnt = cnt
         return pooled
 
     @staticmethod
     def backward(ctx, grad_pooled):
-        x, w, bias, gamma, beta, run_mean, run_var = ctx.saved_tensors
-        with torch.enable_grad():
-            xx = x.detach().requires_grad_(True)
-            ww = w.detach().requires_grad_(True)
-            bb = bias.detach().requires_grad_(True)
-            gg = gamma.detach().requires_grad_(True)
-            be = beta.detach().requires_grad_(True)
-            y = xx @ ww + bb
-            if ctx.training:
-                mean = y.mean(dim=(0, 1)); var = y.var(dim=(0, 1), unbiased=False)
-            else:
-                mean, var = run_mean, run_var
-            out = F.relu((y - mean) * torch.rsqrt(var + BN_EPS) * gg + be).amax(dim=1)
-            grads = torch.autograd.grad(out, (xx, ww, bb, gg, be), grad_pooled)
-        return grads[0], grads[1], grads[2], grads[3], grads[4], None, None, None, None
+        x, w, bias, gamma, inv, mean0, ext0, arg, z = ctx.saved_tensors
+        b, n, k = x.shape
+        c = w.shape[1]
+        s = gamma * inv
+        gt = grad_pooled * (z > 0).to(grad_pooled.dtype)       # (B,C) gradient reaching z at the arg-extremum
+        xhat_star = (ext0 - mean0) * inv
+        dbeta = gt.sum(0)
+        dgamma = (gt * xhat_star).sum(0)
+        sg = gt * s                                            # sparse part of dy, one value per (b,c)
+        idx = arg.long().unsqueeze(-1).expand(b, c, k)
+        xstar = x.gather(1, idx)                               # (B,C,K): the selected points
+        dw = torch.einsum("bck,bc->kc", xstar, sg)
+        dx = torch.zeros_like(x)
+        dx.scatter_add_(1, idx, sg.unsqueeze(-1) * w.t().unsqueeze(0))
+        if ctx.training:
+            t = ctx.cnt
+            q = -s * dgamma * inv / t
+            a = -s * dbeta / t + s * dgamma * mean0 * inv / t
+            x2 = x.reshape(-1, k)
+            gram = x2.t() @ x2                                 # (K,K)
+            dw = dw + torch.outer(x2.sum(0), a) + (gram @ w) * q
+            dx = dx + (x2 @ ((w * q) @ w.t()) + w @ a).view(b, n, k)
+            dbias = torch.zeros_like(bias)                     # BN subtracts the mean: the bias has no effect
+        else:
+            dbias = sg.sum(0)
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 
 
 class SharedMLPLayer(nn.Module):

@@ -188,8 +188,9 @@ def match_cost_factors(xyz1, xyz2, factors, with_grad=True):
 # ---------------------------------------------------------------------------
 # encoder: conv5 + max-pool (models/model.py:57-66)
 # ---------------------------------------------------------------------------
-def encoder_conv_pool(x_bf16, wt_bf16):
-    """x (B,N,K) bf16, wt (C,K) bf16 -> max, min, sum, sumsq of x @ wt.T over the points, each (B,C) fp32"""
+def encoder_conv_pool(x_bf16, wt_bf16, sign=None):
+    """x (B,N,K) bf16, wt (C,K) bf16 -> max, min, sum, sumsq of x @ wt.T over the points, each (B,C) fp32.
+    With `sign` (C,) fp32 also -> arg (B,C) int32: first point attaining the max (sign>=0) / min (sign<0)."""
     _dev(x_bf16, "x"); _dev(wt_bf16, "wt")
     _require(x_bf16.dim() == 3 and wt_bf16.dim() == 2 and x_bf16.shape[2] == wt_bf16.shape[1],
              "encoder_conv_pool expects x (batch,#points,k) and wt (c,k)")
@@ -202,5 +203,11 @@ def encoder_conv_pool(x_bf16, wt_bf16):
     dev = x.device
     with torch.cuda.device(dev):
         outs = [torch.empty((b, c), dtype=torch.float32, device=dev) for _ in range(4)]
-        _lib.check(lib.pnae_encoder_conv_pool(b, n, k, c, _p(x), _p(wt), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _stream(x)))
-    return tuple(outs)
+        arg = None
+        if sign is not None:
+            _require(tuple(sign.shape) == (c,), "encoder_conv_pool expects sign of shape (c,)")
+            sign = _f32c(_dev(sign, "sign"))
+            arg = torch.empty((b, c), dtype=torch.int32, device=dev)
+        _lib.check(lib.pnae_encoder_conv_pool(b, n, k, c, _p(x), _p(wt), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
+                                              _p(sign), _p(arg), _stream(x)))
+    return tuple(outs) if arg is None else tuple(outs) + (arg,)

@@ -116,15 +116,13 @@ class SharedMLPLayer(nn.Module):
         self.register_buffer("moving_var", torch.ones(cout))
 
     def forward(self, x, bn_decay=0.9):
-        y = x @ self.weight + self.bias
-        if self.training:
-            mean = y.mean(dim=(0, 1)); var = y.var(dim=(0, 1), unbiased=False)
-            with torch.no_grad():
-                self.moving_mean.mul_(bn_decay).add_(mean.detach(), alpha=1.0 - bn_decay)
-                self.moving_var.mul_(bn_decay).add_(var.detach(), alpha=1.0 - bn_decay)
-        else:
-            mean, var = self.moving_mean, self.moving_var
-        return F.relu((y - mean) * torch.rsqrt(var + BN_EPS) * self.gamma + self.beta)
+        b, n, _ = x.shape
+        y = torch.addmm(self.bias, x.reshape(b * n, -1), self.weight)
+        # library batch-norm kernel (fused statistics + normalise, fused backward).  Its moving variance
+        # uses the unbiased estimate (x T/(T-1), T = B*N >= 65536 here: 1.5e-5 relative to TF's biased one).
+        y = F.batch_norm(y, self.moving_mean, self.moving_var, self.gamma, self.beta, self.training,
+                         1.0 - bn_decay, BN_EPS)
+        return F.relu(y).view(b, n, -1)
 
 
 class PointNetEncoder(nn.Module):

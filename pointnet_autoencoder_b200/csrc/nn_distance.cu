@@ -105,6 +105,9 @@ nn_fwd_kernel(const FwdParams p)
     __shared__ __align__(16) u64 skey_all[kWarps][kChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *srow = srow_all[warp];
+    // let the finalize launch become resident as SMs drain (it blocks in cudaGridDependencySynchronize
+    // until every CTA of this grid has finished and flushed): its launch latency hides under the sweep's tail
+    asm volatile("griddepcontrol.launch_dependents;");
     const long long wid = (long long)blockIdx.x * kWarps + warp;
     long long u = wid * p.units / p.warps;
     const long long uend = (wid + 1) * p.units / p.warps;
@@ -137,7 +140,6 @@ nn_fwd_kernel(const FwdParams p)
     };
 
     for (; u < uend; u++) {
-        decode(u, e, rb, ch);
         cp_async_wait_all();
         __syncwarp();
         if (e != held_e || rb != held_rb) {
@@ -158,11 +160,10 @@ nn_fwd_kernel(const FwdParams p)
             held_e = e; held_rb = rb; held_u0 = u;
         }
         __syncwarp();      // every lane has its rows in registers: the row buffer may be refilled
-        if (u + 1 < uend) {
-            int e2, rb2, ch2;
-            decode(u + 1, e2, rb2, ch2);
-            prefetch_unit(p, e2, rb2, ch2, srow, scol_all[warp][buf ^ 1], e2 != e || rb2 != rb);
-        }
+        // successor unit without divisions: chunk fastest, then row block, then element
+        int e2 = e, rb2 = rb, ch2 = ch + 1;
+        if (ch2 == p.nch) { ch2 = 0; if (++rb2 == p.nrb) { rb2 = 0; e2++; } }
+        if (u + 1 < uend) prefetch_unit(p, e2, rb2, ch2, srow, scol_all[warp][buf ^ 1], ch2 == 0);
 
         // ---- 256 rows x 32 columns
         const float4 *scol = scol_all[warp][buf];
@@ -213,6 +214,7 @@ nn_fwd_kernel(const FwdParams p)
         const int k = ch * kChunk + lane;
         if (k < p.m) p.colkeys[((size_t)e * p.nrb + rb) * p.m + k] = mykey;
         buf ^= 1;
+        e = e2; rb = rb2; ch = ch2;
     }
     flush_rows();
 }
@@ -234,9 +236,8 @@ nn_finalize_kernel(const FwdParams p)
     constexpr int kPtsPerWarp = 32 / kFinLanes;
     const long long warp_id = ((long long)blockIdx.x * kFinThreads + threadIdx.x) >> 5;
     const long long n_warps = (long long)gridDim.x * kFinThreads >> 5;
-#if __CUDA_ARCH__ >= 900
-    cudaGridDependencySynchronize();      // launched with programmatic stream serialization
-#endif
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // launched with programmatic stream serialization
+    asm volatile("griddepcontrol.launch_dependents;");        // the gradient kernel may queue up behind us the same way
     for (long long base = warp_id * kPtsPerWarp; base < total; base += n_warps * kPtsPerWarp) {   // warp-uniform trip count
         const long long pt = base + (threadIdx.x & 31) / kFinLanes;
         const bool live = pt < total;
@@ -374,6 +375,7 @@ nn_bwd_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *
     const int cs = (int)cluster.num_blocks();
     const int nclusters = gridDim.x / cs;
     const int tid = (int)cluster.block_rank() * kBwdThreads + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: idx comes from the kernel before
     const int stride = cs * kBwdThreads;
     for (int e = blockIdx.x / cs; e < b; e += nclusters) {
         const float *p1 = xyz1 + (size_t)e * n * 3, *p2 = xyz2 + (size_t)e * m * 3;
@@ -474,13 +476,15 @@ extern "C" int pnae_nn_distance_bwd(int b, int n, const float *xyz1, int m, cons
     cfg.gridDim = dim3((unsigned)(nclusters * cs));
     cfg.blockDim = dim3(kBwdThreads);
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_bwd_kernel, b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2,
                                     grad_xyz1, grad_xyz2));
     return PNAE_OK;

@@ -237,18 +237,23 @@ def run_product(args):
     # One CUDA graph per ring slot: NnDistance + NnDistanceGrad through the C ABI (3 kernels), replayed
     # with one launch per step -- the step is launch-bound otherwise (pointnet_autoencoder_b200/graphs.py).
     from pointnet_autoencoder_b200.graphs import ChamferStep
-    slots = [ChamferStep(x1[i], x2[i], g1, g2) for i in range(RING)]
+    SPG = args.steps_per_graph      # consecutive steps captured per graph (launch overhead amortised over SPG steps)
+    assert RING % SPG == 0 and args.steps % SPG == 0 and args.warmup % SPG == 0, "steps/warmup must be multiples of --steps-per-graph"
+    grp = lambda t, g: [t[g * SPG + j] for j in range(SPG)]
+    slots = [ChamferStep(grp(x1, 0), grp(x2, 0), g1, g2)]
+    slots += [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, share_buffers_with=slots[0]) for g in range(1, RING // SPG)]   # new inputs, same outputs/workspace
 
     # the dominant kernel pair alone (sweep + finalize), for the roofline figure
-    fwd_slots = [ChamferStep(x1[i], x2[i], g1, g2, forward_only=True) for i in range(RING)]
+    fwd_slots = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, forward_only=True, share_buffers_with=slots[0]) for g in range(RING // SPG)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        slots[i % RING].run()
+    NG = RING // SPG
+    for i in range(args.warmup // SPG):
+        slots[i % NG].run()
     barrier()
 
     sampler = ClockSampler(local)
@@ -259,14 +264,14 @@ def run_product(args):
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
-        slots[i % RING].run()
+    for i in range(args.steps // SPG):
+        slots[i % NG].run()
     e1.record(stream)
     barrier()
     # forward alone, same ring, same clocks: CUDA events on the launching stream
     f0.record(stream)
-    for i in range(args.steps):
-        fwd_slots[i % RING].run()
+    for i in range(args.steps // SPG):
+        fwd_slots[i % NG].run()
     f1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -319,8 +324,8 @@ def run_product(args):
         "dtype": "f32", "data": "synthetic (S-randn, seed 100+rank; mirrors tf_nndistance.py:45-49)",
         "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
                    "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
-                   "l2": "ring of %d distinct batches (%.0f MB touched) > 126 MB L2" % (RING, RING * (alg_bytes + 12 * B * (N + M)) / 1e6),
-                   "launch": "one CUDA graph replay per step (3 kernels: sweep, finalize, gradient)",
+                   "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB) > 126 MB L2; outputs and workspace are reused" % (RING, RING * 12 * B * (N + M) / 1e6),
+                   "launch": "CUDA graphs of %d consecutive steps (3 kernels per step: sweep, finalize, gradient), one replay per %d steps" % (SPG, SPG),
                    "upstream_grad": "100/(B*N) (models/model.py:81-83)"},
         "roofline": {"bound": "fp32", "kernel": "nn_distance forward (nn_fwd_kernel sweep + nn_finalize_kernel)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak, "traffic": 1606400,
@@ -376,7 +381,12 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-emd", action="store_true")
+    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide 64, steps and warmup)")
     args = ap.parse_args()
+    if args.impl != "reference":
+        spg = args.steps_per_graph
+        args.steps = max(spg, (args.steps + spg - 1) // spg * spg)      # whole graphs only; the JSON line reports the steps actually run
+        args.warmup = max(spg, (args.warmup + spg - 1) // spg * spg)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -81,6 +81,13 @@ PNAE_API int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m, c
                                        const float *grad_dist1, const float *grad_dist2,
                                        float *grad_xyz1, float *grad_xyz2,
                                        void *workspace, size_t workspace_bytes, void **handle);
+/* The same for `steps` consecutive steps over different inputs (xyz1[s], xyz2[s]) and shared outputs: one
+ * launch replays them back to back (results of the last step remain in the output buffers). */
+PNAE_API int pnae_chamfer_graph_create_multi(int steps, int b, int n, const float *const *xyz1, int m, const float *const *xyz2,
+                                             float *dist1, int *idx1, float *dist2, int *idx2,
+                                             const float *grad_dist1, const float *grad_dist2,
+                                             float *grad_xyz1, float *grad_xyz2,
+                                             void *workspace, size_t workspace_bytes, void **handle);
 PNAE_API int pnae_graph_launch(void *handle, void *stream);
 PNAE_API int pnae_graph_destroy(void *handle);
 

@@ -234,7 +234,10 @@ nn_fwd_kernel(const FwdParams p)
 // point of xyz2) with the same arithmetic as the sweep; the lowest index whose distance equals
 // the minimum is the reference's first argmin.  All loads of a phase are independent, so a
 // point costs two dependent L2 round trips.
-constexpr int kFinLanes = 4;
+#ifndef PNAE_NN_FINLANES
+#define PNAE_NN_FINLANES 4
+#endif
+constexpr int kFinLanes = PNAE_NN_FINLANES;
 constexpr int kFinThreads = 256;
 
 __global__ void __launch_bounds__(kFinThreads, 4)
@@ -409,8 +412,9 @@ nn_bwd_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *
                     atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
                 }
             }
-            __threadfence();
-            cluster.sync();
+            // the barrier orders phase 1's plain stores before phase 2's atomics on the same addresses
+            // (release/acquire at cluster scope; all of an element's traffic stays inside its cluster)
+            if (phase == 0) cluster.sync();
         }
     }
 }
@@ -510,13 +514,14 @@ struct PnaeGraph {
     cudaGraphExec_t exec;
 };
 
-extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m, const float *xyz2,
-                                         float *dist1, int *idx1, float *dist2, int *idx2,
-                                         const float *grad_dist1, const float *grad_dist2,
-                                         float *grad_xyz1, float *grad_xyz2,
-                                         void *workspace, size_t workspace_bytes, void **handle)
+extern "C" int pnae_chamfer_graph_create_multi(int steps, int b, int n, const float *const *xyz1, int m, const float *const *xyz2,
+                                               float *dist1, int *idx1, float *dist2, int *idx2,
+                                               const float *grad_dist1, const float *grad_dist2,
+                                               float *grad_xyz1, float *grad_xyz2,
+                                               void *workspace, size_t workspace_bytes, void **handle)
 {
     PNAE_REQUIRE(handle != nullptr, "chamfer_graph_create: NULL handle");
+    PNAE_REQUIRE(steps >= 1 && xyz1 && xyz2, "chamfer_graph_create: need steps >= 1 and input pointer lists");
     *handle = nullptr;
     cudaStream_t st;
     PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -528,9 +533,11 @@ extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m,
         pnae_set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
         return PNAE_ERR_CUDA;
     }
-    rc = pnae_nn_distance_fwd(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, st);
-    if (rc == PNAE_OK && grad_xyz1 != nullptr && grad_xyz2 != nullptr)     // NULL gradients: forward only
-        rc = pnae_nn_distance_bwd(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, st);
+    for (int s = 0; s < steps && rc == PNAE_OK; s++) {
+        rc = pnae_nn_distance_fwd(b, n, xyz1[s], m, xyz2[s], dist1, idx1, dist2, idx2, workspace, workspace_bytes, st);
+        if (rc == PNAE_OK && grad_xyz1 != nullptr && grad_xyz2 != nullptr)     // NULL gradients: forward only
+            rc = pnae_nn_distance_bwd(b, n, xyz1[s], m, xyz2[s], grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, st);
+    }
     ce = cudaStreamEndCapture(st, &graph);
     cudaStreamDestroy(st);
     if (rc != PNAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -548,6 +555,16 @@ extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m,
     PnaeGraph *g = new PnaeGraph{graph, exec};
     *handle = g;
     return PNAE_OK;
+}
+
+extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                         float *dist1, int *idx1, float *dist2, int *idx2,
+                                         const float *grad_dist1, const float *grad_dist2,
+                                         float *grad_xyz1, float *grad_xyz2,
+                                         void *workspace, size_t workspace_bytes, void **handle)
+{
+    return pnae_chamfer_graph_create_multi(1, b, n, &xyz1, m, &xyz2, dist1, idx1, dist2, idx2, grad_dist1, grad_dist2,
+                                           grad_xyz1, grad_xyz2, workspace, workspace_bytes, handle);
 }
 
 extern "C" int pnae_graph_launch(void *handle, void *stream)

@@ -24,8 +24,15 @@ class ChamferStep:
 
     kernels_per_run = 3     # sweep, finalize, gradient
 
-    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False):
-        assert xyz1.is_cuda and xyz2.is_cuda and xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32
+    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None):
+        # xyz1 / xyz2 may be LISTS of equally shaped tensors: the graph then holds that many consecutive steps
+        # (one per input pair, all writing the same output buffers) and one run() replays them back to back
+        multi1 = list(xyz1) if isinstance(xyz1, (list, tuple)) else [xyz1]
+        multi2 = list(xyz2) if isinstance(xyz2, (list, tuple)) else [xyz2]
+        assert len(multi1) == len(multi2) and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in multi1 + multi2)
+        self.steps = len(multi1)
+        self._inputs = (multi1, multi2)
+        xyz1, xyz2 = multi1[0], multi2[0]
         self.xyz1 = xyz1.contiguous()
         self.xyz2 = xyz2.contiguous()
         b, n, _ = self.xyz1.shape
@@ -35,20 +42,29 @@ class ChamferStep:
         f32 = dict(dtype=torch.float32, device=dev); i32 = dict(dtype=torch.int32, device=dev)
         self.g1 = grad_dist1 if grad_dist1 is not None else torch.full((b, n), 100.0 / (b * n), **f32)
         self.g2 = grad_dist2 if grad_dist2 is not None else torch.full((b, m), 100.0 / (b * m), **f32)
-        self.dist1 = torch.empty((b, n), **f32); self.idx1 = torch.empty((b, n), **i32)
-        self.dist2 = torch.empty((b, m), **f32); self.idx2 = torch.empty((b, m), **i32)
-        self.grad_xyz1 = torch.empty((b, n, 3), **f32); self.grad_xyz2 = torch.empty((b, m, 3), **f32)
         lib = _lib.load()
+        o = share_buffers_with          # another ChamferStep of the same shape: reuse its outputs and workspace
+        if o is not None:               # (steps that run one after another on one stream, e.g. a ring of input batches)
+            assert o.dist1.shape == (b, n) and o.dist2.shape == (b, m) and o.device == dev
+            self.dist1, self.idx1, self.dist2, self.idx2 = o.dist1, o.idx1, o.dist2, o.idx2
+            self.grad_xyz1, self.grad_xyz2, self.ws = o.grad_xyz1, o.grad_xyz2, o.ws
+        else:
+            self.dist1 = torch.empty((b, n), **f32); self.idx1 = torch.empty((b, n), **i32)
+            self.dist2 = torch.empty((b, m), **f32); self.idx2 = torch.empty((b, m), **i32)
+            self.grad_xyz1 = torch.empty((b, n, 3), **f32); self.grad_xyz2 = torch.empty((b, m, 3), **f32)
         with torch.cuda.device(dev):
             wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
-            self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+            if o is None:
+                self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize(dev)
             h = C.c_void_p()
             p = lambda t: C.c_void_p(t.data_ptr())
-            _lib.check(lib.pnae_chamfer_graph_create(b, n, p(self.xyz1), m, p(self.xyz2), p(self.dist1), p(self.idx1),
-                                                     p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),
-                                                     None if forward_only else p(self.grad_xyz1),
-                                                     None if forward_only else p(self.grad_xyz2), p(self.ws), wsb, C.byref(h)))
+            arr1 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi1])
+            arr2 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi2])
+            _lib.check(lib.pnae_chamfer_graph_create_multi(self.steps, b, n, arr1, m, arr2, p(self.dist1), p(self.idx1),
+                                                           p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),
+                                                           None if forward_only else p(self.grad_xyz1),
+                                                           None if forward_only else p(self.grad_xyz2), p(self.ws), wsb, C.byref(h)))
         self._h = h
         self._lib = lib
 

@@ -65,6 +65,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (train.py default 32)")
     ap.add_argument("--unfused-encoder", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph per step")
+    ap.add_argument("--tf32", action="store_true", help="let the LIBRARY GEMMs/convs (decoder, encoder layers 1-4) use TF32 tensor cores")
     args = ap.parse_args()
     if args.cpu_baseline:
         return cpu_baseline(args)
@@ -80,6 +82,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                                   # identical initial replicas
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     n = 2048
     if args.model == "upconv":
         model = models.AutoEncoderUpconv(fused_encoder=not args.unfused_encoder).to(dev)
@@ -87,24 +91,52 @@ def main():
         model = models.AutoEncoderFC(num_point=n, fused_encoder=not args.unfused_encoder).to(dev)
     loss_fn = models.emd_loss if args.model == "emd" else models.chamfer_loss
     bucket = parallel.GradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, eps=1e-8)
+    use_graph = not args.no_graph
+    lr_t = torch.tensor(1e-3, device=dev)                  # tensor LR: the schedule can change it without re-capturing
+    opt = torch.optim.Adam(model.parameters(), lr=lr_t if use_graph else 1e-3, eps=1e-8, capturable=use_graph)
     gb = args.batch * world
     # each replica's own shard of the synthetic "dataset": pinned host clouds, copied in every step
     label, _ = synthetic.s_chair(args.batch * 4, n, first_id=rank * args.batch * 4)
     host = torch.from_numpy(label).pin_memory()
     x = torch.empty((args.batch, n, 3), device=dev)
 
-    def step(i):
-        x.copy_(host[(i % 4) * args.batch:(i % 4 + 1) * args.batch], non_blocking=True)
-        for g in opt.param_groups:
-            g["lr"] = models.get_learning_rate(i, gb)
-        pred, _ = model(x, models.get_bn_decay(i, gb))
+    loss_buf = torch.zeros((), device=dev)
+
+    def compute(bn_decay):
+        pred, _ = model(x, bn_decay)
         loss, pcloss = loss_fn(pred, x)
         bucket.zero()
         loss.backward()
         bucket.all_reduce()
         opt.step()
-        return loss
+        loss_buf.copy_(loss.detach())
+
+    graphs = {}                                            # one captured step per BN-decay value (it changes every ~200k samples)
+
+    def step(i):
+        x.copy_(host[(i % 4) * args.batch:(i % 4 + 1) * args.batch], non_blocking=True)
+        lr = models.get_learning_rate(i, gb)
+        bn_decay = models.get_bn_decay(i, gb)
+        if not use_graph:
+            for g in opt.param_groups:
+                g["lr"] = lr
+            compute(bn_decay)
+            return loss_buf
+        lr_t.fill_(lr)
+        if bn_decay not in graphs:
+            s_ = torch.cuda.Stream(device=dev)
+            s_.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s_):
+                for _ in range(3):                         # warm-up outside capture (allocator, NCCL, cuDNN autotune)
+                    compute(bn_decay)
+            torch.cuda.current_stream(dev).wait_stream(s_)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                compute(bn_decay)
+            graphs[bn_decay] = g
+        graphs[bn_decay].replay()
+        return loss_buf
 
     for i in range(args.warmup):
         step(i)
@@ -135,7 +167,7 @@ def main():
                                      "global_batch": gb, "per_gpu_batch": args.batch, "params": nparam,
                                      "grad_allreduce_bytes": 4 * nparam if world > 1 else 0,
                                      "parallelism": "dp%d, one NCCL all-reduce of the flat gradient bucket per step" % world,
-                                     "fused_encoder": not args.unfused_encoder}}))
+                                     "fused_encoder": not args.unfused_encoder, "cuda_graph_step": use_graph, "library_tf32": bool(args.tf32)}}))
     if world > 1:
         dist.destroy_process_group()
 

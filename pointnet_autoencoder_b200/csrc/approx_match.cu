@@ -31,10 +31,19 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef PNAE_AM_THREADS
+#define PNAE_AM_THREADS 256
+#endif
+#ifndef PNAE_AM_TS
+#define PNAE_AM_TS 128
+#endif
+#ifndef PNAE_AM_CTAS
+#define PNAE_AM_CTAS 2
+#endif
+constexpr int kThreads = PNAE_AM_THREADS;
 constexpr int kOwn = 2 * kThreads;     // own points per task: one packed pair per thread
-constexpr int kTs = 128;               // streamed points per task
-constexpr int kCtasPerSm = 2;
+constexpr int kTs = PNAE_AM_TS;        // streamed points per task
+constexpr int kCtasPerSm = PNAE_AM_CTAS;
 constexpr int kLevels = PNAE_NUM_LEVELS;
 
 struct EmdParams {

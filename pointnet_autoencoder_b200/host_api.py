@@ -68,6 +68,74 @@ class ChamferHostRunner:
         return {k: v.numpy() for k, v in self.h_out.items()}
 
 
+class ChamferHostPipeline:
+    """Streaming form of ChamferHostRunner: `depth` buffer sets and three streams so that the
+    host->device copy of step i+1, the kernels of step i and the device->host copy of step i-1
+    overlap (PCIe both directions + SMs busy at once).  Every step still moves all of its inputs
+    in and all of its results out.
+
+        pipe = ChamferHostPipeline(B, N, M)
+        for xyz1, xyz2 in batches:                 # pinned host tensors (or numpy arrays)
+            done = pipe.submit(xyz1, xyz2)         # -> results of the step that just retired, or None
+        for done in pipe.drain(): ...
+
+    Results are dicts of numpy views on pinned buffers, valid until the next submit()."""
+
+    def __init__(self, b, n, m, device="cuda", depth=4):
+        self.device = torch.device(device)
+        self.depth = depth
+        with torch.cuda.device(self.device):
+            self.s_in = torch.cuda.Stream(device=self.device)
+            self.s_run = torch.cuda.Stream(device=self.device)
+            self.s_out = torch.cuda.Stream(device=self.device)
+            self.sets = []
+            for _ in range(depth):
+                r = ChamferHostRunner(b, n, m, self.device)          # its own inputs, outputs, graph, pinned results
+                r.ev_in = torch.cuda.Event(); r.ev_run = torch.cuda.Event(); r.ev_out = torch.cuda.Event()
+                r.busy = False
+                self.sets.append(r)
+        self.h2d_bytes = self.sets[0].h2d_bytes
+        self.d2h_bytes = self.sets[0].d2h_bytes
+        self.count = 0
+
+    def _retire(self, r):
+        r.ev_out.synchronize()
+        r.busy = False
+        return {k: v.numpy() for k, v in r.h_out.items()}
+
+    def submit(self, xyz1, xyz2):
+        r = self.sets[self.count % self.depth]
+        assert not r.busy
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(self.s_in):
+                r.d_xyz1.copy_(r._stage(xyz1, r.h_xyz1), non_blocking=True)
+                r.d_xyz2.copy_(r._stage(xyz2, r.h_xyz2), non_blocking=True)
+                r.ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(r.ev_in)
+                st = r.graph_step.run()
+                r.ev_run.record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(r.ev_run)
+                for k, t in (("dist1", st.dist1), ("idx1", st.idx1), ("dist2", st.dist2), ("idx2", st.idx2),
+                             ("grad_xyz1", st.grad_xyz1), ("grad_xyz2", st.grad_xyz2)):
+                    r.h_out[k].copy_(t, non_blocking=True)
+                r.ev_out.record(self.s_out)
+        r.busy = True
+        self.count += 1
+        # free the buffer set the NEXT submit will use: its results stay valid until that submit
+        nxt = self.sets[self.count % self.depth]
+        return self._retire(nxt) if nxt.busy else None
+
+    def drain(self):
+        out = []
+        for i in range(self.depth):
+            r = self.sets[(self.count + i) % self.depth]
+            if r.busy:
+                out.append(self._retire(r))
+        return out
+
+
 def nn_distance_host(xyz1, xyz2, grad_dist1=None, grad_dist2=None):
     """One-shot convenience wrapper: numpy in -> dict of numpy arrays (copies)."""
     xyz1 = np.ascontiguousarray(xyz1, np.float32); xyz2 = np.ascontiguousarray(xyz2, np.float32)

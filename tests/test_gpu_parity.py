@@ -99,6 +99,28 @@ def test_chamfer_graph_step_equals_eager_calls():
     assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
 
 
+def test_host_pipeline_matches_eager():
+    from pointnet_autoencoder_b200 import host_api
+    b, n, m = 2, 300, 200
+    pipe = host_api.ChamferHostPipeline(b, n, m, depth=3)
+    batches = [synthetic.s_randn(b, n, m, seed=s) for s in range(7)]
+    outs = []
+    for a, c in batches:
+        r = pipe.submit(a, c)
+        if r is not None:
+            outs.append({k: v.copy() for k, v in r.items()})
+    outs += [{k: v.copy() for k, v in r.items()} for r in pipe.drain()]
+    assert len(outs) == 7
+    for (a, c), r in zip(batches, outs):        # results come back in submission order
+        od1, oi1, od2, oi2 = O.nn_distance(a, c)
+        assert np.array_equal(r["dist1"], od1) and np.array_equal(r["idx1"], oi1)
+        assert np.array_equal(r["dist2"], od2) and np.array_equal(r["idx2"], oi2)
+        g = np.full((b, n), 100.0 / (b * n), np.float32); g2 = np.full((b, m), 100.0 / (b * m), np.float32)
+        o1, o2 = O.nn_distance_grad(a, c, g, oi1, g2, oi2)
+        np.testing.assert_allclose(r["grad_xyz1"], o1, rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(r["grad_xyz2"], o2, rtol=1e-4, atol=1e-7)
+
+
 def test_nn_distance_chamfer_loss_grad_constant():
     # models/model.py:81-83: loss = 100*mean(dist1+dist2) -> upstream grad 100/(B*N)
     label, pred = synthetic.s_chair(2, 1024)

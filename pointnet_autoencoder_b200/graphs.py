@@ -24,7 +24,7 @@ class ChamferStep:
 
     kernels_per_run = 3     # sweep, finalize, gradient
 
-    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None):
+    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None, outputs=None):
         # xyz1 / xyz2 may be LISTS of equally shaped tensors: the graph then holds that many consecutive steps
         # (one per input pair, all writing the same output buffers) and one run() replays them back to back
         multi1 = list(xyz1) if isinstance(xyz1, (list, tuple)) else [xyz1]
@@ -48,6 +48,10 @@ class ChamferStep:
             assert o.dist1.shape == (b, n) and o.dist2.shape == (b, m) and o.device == dev
             self.dist1, self.idx1, self.dist2, self.idx2 = o.dist1, o.idx1, o.dist2, o.idx2
             self.grad_xyz1, self.grad_xyz2, self.ws = o.grad_xyz1, o.grad_xyz2, o.ws
+        elif outputs is not None:       # caller-provided output tensors (e.g. views into one flat buffer)
+            self.dist1, self.idx1, self.dist2, self.idx2 = outputs["dist1"], outputs["idx1"], outputs["dist2"], outputs["idx2"]
+            self.grad_xyz1, self.grad_xyz2 = outputs["grad_xyz1"], outputs["grad_xyz2"]
+            assert all(t.is_contiguous() and t.device == dev for t in outputs.values())
         else:
             self.dist1 = torch.empty((b, n), **f32); self.idx1 = torch.empty((b, n), **i32)
             self.dist2 = torch.empty((b, m), **f32); self.idx2 = torch.empty((b, m), **i32)

@@ -33,15 +33,23 @@ class ChamferHostRunner:
         self.d_xyz2 = torch.empty((b, m, 3), dtype=torch.float32, device=self.device)
         self.g1 = torch.full((b, n), 100.0 / (b * n), device=self.device)
         self.g2 = torch.full((b, m), 100.0 / (b * m), device=self.device)
+        # all results live in ONE flat device buffer mirrored by ONE pinned host buffer: a step's
+        # device->host traffic is a single copy
+        spec = [("dist1", (b, n), torch.float32), ("idx1", (b, n), torch.int32), ("dist2", (b, m), torch.float32),
+                ("idx2", (b, m), torch.int32), ("grad_xyz1", (b, n, 3), torch.float32), ("grad_xyz2", (b, m, 3), torch.float32)]
+        offs, total = {}, 0
+        for name, shape, dt in spec:
+            offs[name] = total
+            total += (int(np.prod(shape)) * 4 + 255) // 256 * 256
+        self.d_flat = torch.empty((total,), dtype=torch.uint8, device=self.device)
+        self.h_flat = torch.empty((total,), dtype=torch.uint8, pin_memory=True)
+        carve = lambda flat, name, shape, dt: flat[offs[name]: offs[name] + int(np.prod(shape)) * 4].view(dt).view(shape)
+        self.d_out = {name: carve(self.d_flat, name, shape, dt) for name, shape, dt in spec}
+        self.h_out = {name: carve(self.h_flat, name, shape, dt) for name, shape, dt in spec}
         with torch.cuda.device(self.device):
-            self.graph_step = ChamferStep(self.d_xyz1, self.d_xyz2, self.g1, self.g2)   # one launch per step
-        self.h_out = {
-            "dist1": _pinned((b, n), torch.float32), "idx1": _pinned((b, n), torch.int32),
-            "dist2": _pinned((b, m), torch.float32), "idx2": _pinned((b, m), torch.int32),
-            "grad_xyz1": _pinned((b, n, 3), torch.float32), "grad_xyz2": _pinned((b, m, 3), torch.float32),
-        }
+            self.graph_step = ChamferStep(self.d_xyz1, self.d_xyz2, self.g1, self.g2, outputs=self.d_out)   # one launch per step
         self.h2d_bytes = 4 * 3 * b * (n + m)
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
+        self.d2h_bytes = sum(int(np.prod(shape)) * 4 for _, shape, _ in spec)
 
     def _stage(self, src, pinned):
         if isinstance(src, torch.Tensor):
@@ -60,10 +68,8 @@ class ChamferHostRunner:
                 self.g1.copy_(torch.as_tensor(grad_dist1, dtype=torch.float32), non_blocking=True)
             if grad_dist2 is not None:
                 self.g2.copy_(torch.as_tensor(grad_dist2, dtype=torch.float32), non_blocking=True)
-            st = self.graph_step.run()
-            d1, i1, d2, i2, o1, o2 = st.dist1, st.idx1, st.dist2, st.idx2, st.grad_xyz1, st.grad_xyz2
-            for k, t in (("dist1", d1), ("idx1", i1), ("dist2", d2), ("idx2", i2), ("grad_xyz1", o1), ("grad_xyz2", o2)):
-                self.h_out[k].copy_(t, non_blocking=True)
+            self.graph_step.run()
+            self.h_flat.copy_(self.d_flat, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return {k: v.numpy() for k, v in self.h_out.items()}
 
@@ -113,13 +119,11 @@ class ChamferHostPipeline:
                 r.ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(r.ev_in)
-                st = r.graph_step.run()
+                r.graph_step.run()
                 r.ev_run.record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(r.ev_run)
-                for k, t in (("dist1", st.dist1), ("idx1", st.idx1), ("dist2", st.dist2), ("idx2", st.idx2),
-                             ("grad_xyz1", st.grad_xyz1), ("grad_xyz2", st.grad_xyz2)):
-                    r.h_out[k].copy_(t, non_blocking=True)
+                r.h_flat.copy_(r.d_flat, non_blocking=True)
                 r.ev_out.record(self.s_out)
         r.busy = True
         self.count += 1

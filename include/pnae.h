@@ -72,6 +72,16 @@ PNAE_API int pnae_nn_distance_bwd(int b, int n, const float *xyz1, int m, const 
                          const float *grad_dist2, const int *idx2,
                          float *grad_xyz1, float *grad_xyz2, void *stream);
 
+/* Fused Chamfer loss + gradient (the loss of models/model.py:80-83 without the op seam):
+ *   *loss      = w1 * sum(dist1) + w2 * sum(dist2)          (model.py: w1 = 100/(b*n), w2 = 100/(b*m))
+ *   grad_xyz1/2 = d loss / d xyz1, d loss / d xyz2           ((b,n,3), (b,m,3), fully overwritten)
+ * in the two launches of the forward (no gradient launch, no dist/idx round trip).  dist1/idx1 and
+ * dist2/idx2 are optional outputs (NULL pairs to skip).  Same workspace as pnae_nn_distance_fwd. */
+PNAE_API int pnae_chamfer_loss_grad(int b, int n, const float *xyz1, int m, const float *xyz2, float w1, float w2,
+                                    float *loss, float *grad_xyz1, float *grad_xyz2,
+                                    float *dist1, int *idx1, float *dist2, int *idx2,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* One Chamfer step (pnae_nn_distance_fwd + pnae_nn_distance_bwd over FIXED buffers) captured into a
  * CUDA graph: at B=32, N=M=2048 the step is three kernels and ~80 us of GPU time, so one launch per
  * step instead of three is the difference between GPU-bound and host-bound.  The handle owns only

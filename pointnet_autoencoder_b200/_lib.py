@@ -32,6 +32,7 @@ SIGNATURES = {
     "pnae_nn_distance_workspace_bytes": (_sz, [_i, _i, _i]),
     "pnae_nn_distance_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pnae_nn_distance_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnae_chamfer_loss_grad": (_i, [_i, _i, _vp, _i, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pnae_chamfer_graph_create": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_graph_create_multi": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_graph_launch": (_i, [_vp, _vp]),

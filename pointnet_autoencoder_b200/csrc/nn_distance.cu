@@ -53,6 +53,11 @@ struct FwdParams {
     int *idx1, *idx2;
     u64 *rowkeys;      // [be][nrb][nslot][256]  (min bits << 32 | chunk index)
     u64 *colkeys;      // [be][nrb][m]           (min bits << 32 | ballot of lanes holding the min)
+    // fused loss + gradient (pnae_chamfer_loss_grad); all NULL/0 on the plain forward path
+    float *loss;       // [1]      += w1*sum(dist1) + w2*sum(dist2)
+    float *gxyz1, *gxyz2;   // (be,n,3), (be,m,3): d loss / d xyz, zeroed by the sweep, accumulated by the finalize
+    float w1, w2;
+    int zero_loss;     // this launch is the first chunk of the call: it also zeroes *loss
 };
 
 // three-input minimum (FMNMX3); NaN operands are ignored like fminf
@@ -116,6 +121,14 @@ nn_fwd_kernel(const FwdParams p)
     // let the finalize launch become resident as SMs drain (it blocks in cudaGridDependencySynchronize
     // until every CTA of this grid has finished and flushed): its launch latency hides under the sweep's tail
     asm volatile("griddepcontrol.launch_dependents;");
+    if (p.gxyz1 != nullptr) {
+        // fused loss+gradient: the finalize accumulates into these with atomics, so clear them here (it cannot
+        // start touching them before this whole grid has finished)
+        const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+        for (long long i = tid; i < (long long)p.be * p.n * 3; i += nt) p.gxyz1[i] = 0.f;
+        for (long long i = tid; i < (long long)p.be * p.m * 3; i += nt) p.gxyz2[i] = 0.f;
+        if (tid == 0 && p.zero_loss) *p.loss = 0.f;
+    }
     const long long wid = (long long)blockIdx.x * kWarps + warp;
     long long u = wid * p.units / p.warps;
     const long long uend = (wid + 1) * p.units / p.warps;
@@ -240,10 +253,19 @@ nn_fwd_kernel(const FwdParams p)
 constexpr int kFinLanes = PNAE_NN_FINLANES;
 constexpr int kFinThreads = 256;
 
+// FUSED: additionally accumulate loss = w1*sum(dist1) + w2*sum(dist2) and its gradient
+//   d/d a_j = 2 w (a_j - c_nn(j)),   d/d c_nn(j) = -2 w (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148 with
+// grad_dist == w), so the Chamfer loss of models/model.py:80-83 needs no separate gradient launch and no dist/idx
+// round trip.  dist/idx outputs are optional on this path.
+template <bool FUSED>
 __global__ void __launch_bounds__(kFinThreads, 4)
 nn_finalize_kernel(const FwdParams p)
 {
+    float loss_acc = 0.f;
     const int sub = threadIdx.x & (kFinLanes - 1);
+    // shuffles stay inside one point's lane group: a warp whose points straddle the xyz1/xyz2 boundary of an
+    // element (n not a multiple of 32/kFinLanes) takes both branches below, so a full-warp mask would be divergent
+    const unsigned gmask = ((1u << kFinLanes) - 1u) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
     const long long per_e = (long long)p.n + p.m;
     const long long total = (long long)p.be * per_e;
     constexpr int kPtsPerWarp = 32 / kFinLanes;
@@ -277,7 +299,7 @@ nn_finalize_kernel(const FwdParams p)
                 for (int t = 0; t < 8; t++) key = min(key, v[t]);
             }
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(0xffffffffu, key, o));
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
             const float want = __uint_as_float((unsigned)(key >> 32));
             const int k0 = (int)(unsigned)key * kChunk;
             constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
@@ -292,10 +314,22 @@ nn_finalize_kernel(const FwdParams p)
             for (int c = kPer - 1; c >= 0; c--)
                 if (pnae_sqdist(cx[c] - x, cy[c] - y, cz[c] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
             if (live && sub == 0) {
-                p.dist1[(size_t)e * p.n + j] = want;
-                p.idx1[(size_t)e * p.n + j] = found == 0x7fffffff ? min(k0, p.m - 1) : found;
+                const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
+                if (p.dist1 != nullptr) {
+                    p.dist1[(size_t)e * p.n + j] = want;
+                    p.idx1[(size_t)e * p.n + j] = nn;
+                }
+                if (FUSED) {
+                    loss_acc = fmaf(p.w1, want, loss_acc);
+                    const float g = __fmul_rn(p.w1, 2.0f);
+                    float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
         } else {
             // point k of xyz2 -> dist2 / idx2
@@ -316,8 +350,8 @@ nn_finalize_kernel(const FwdParams p)
             }
 #pragma unroll
             for (int o = kFinLanes / 2; o > 0; o >>= 1) {
-                const u64 k2 = __shfl_xor_sync(0xffffffffu, key, o);
-                const unsigned w2 = __shfl_xor_sync(0xffffffffu, who, o);
+                const u64 k2 = __shfl_xor_sync(gmask, key, o);
+                const unsigned w2 = __shfl_xor_sync(gmask, who, o);
                 if (k2 < key) { key = k2; who = w2; }
             }
             const int rbw = (int)(unsigned)key;
@@ -332,12 +366,28 @@ nn_finalize_kernel(const FwdParams p)
                 if (d == want) found = j;
             }
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
             if (live && sub == 0) {
-                p.dist2[(size_t)e * p.m + k] = want;
-                p.idx2[(size_t)e * p.m + k] = found == 0x7fffffff ? min(j0, p.n - 1) : found;
+                const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
+                if (p.dist2 != nullptr) {
+                    p.dist2[(size_t)e * p.m + k] = want;
+                    p.idx2[(size_t)e * p.m + k] = nn;
+                }
+                if (FUSED) {
+                    loss_acc = fmaf(p.w2, want, loss_acc);
+                    const float g = __fmul_rn(p.w2, 2.0f);
+                    float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
         }
+    }
+    if (FUSED) {
+        loss_acc = warp_sum(loss_acc);
+        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(p.loss, loss_acc);
     }
 }
 
@@ -427,20 +477,20 @@ extern "C" size_t pnae_nn_distance_workspace_bytes(int b, int n, int m)
     return make_plan(b, n, m, pnae_sm_count()).total;
 }
 
-extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
-                                    float *dist1, int *idx1, float *dist2, int *idx2,
-                                    void *workspace, size_t workspace_bytes, void *stream)
+namespace {
+// shared launcher: plain forward (loss == NULL) or fused loss + gradient
+int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const float *xyz2,
+               float *dist1, int *idx1, float *dist2, int *idx2,
+               float *loss, float *gxyz1, float *gxyz2, float w1, float w2,
+               void *workspace, size_t workspace_bytes, void *stream)
 {
-    PNAE_REQUIRE(b >= 0 && n >= 1 && m >= 1, "nn_distance: need b>=0, n>=1, m>=1 (got b=%d n=%d m=%d)", b, n, m);
-    PNAE_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "nn_distance: NULL pointer");
-    if (b == 0) return PNAE_OK;
     const int sms = pnae_sm_count();
     const FwdPlan pl = make_plan(b, n, m, sms);
     if (workspace == nullptr || workspace_bytes < pl.total) {
-        pnae_set_error("nn_distance: workspace too small (%zu < %zu bytes)", workspace_bytes, pl.total);
+        pnae_set_error("%s: workspace too small (%zu < %zu bytes)", op, workspace_bytes, pl.total);
         return PNAE_ERR_WORKSPACE;
     }
-    PNAE_REQUIRE(pnae_aligned(workspace, 8), "nn_distance: workspace must be 8-byte aligned");
+    PNAE_REQUIRE(pnae_aligned(workspace, 8), "%s: workspace must be 8-byte aligned", op);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     for (int e0 = 0; e0 < b; e0 += pl.be) {
@@ -450,28 +500,56 @@ extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, cons
         p.units = (long long)p.be * pl.nrb * pl.nch;
         p.warps = pl.warps;
         p.xyz1 = xyz1 + (size_t)e0 * n * 3; p.xyz2 = xyz2 + (size_t)e0 * m * 3;
-        p.dist1 = dist1 + (size_t)e0 * n; p.idx1 = idx1 + (size_t)e0 * n;
-        p.dist2 = dist2 + (size_t)e0 * m; p.idx2 = idx2 + (size_t)e0 * m;
+        p.dist1 = dist1 ? dist1 + (size_t)e0 * n : nullptr; p.idx1 = idx1 ? idx1 + (size_t)e0 * n : nullptr;
+        p.dist2 = dist2 ? dist2 + (size_t)e0 * m : nullptr; p.idx2 = idx2 ? idx2 + (size_t)e0 * m : nullptr;
         p.rowkeys = (u64 *)ws;
         p.colkeys = (u64 *)(ws + pl.row_bytes);
+        p.loss = loss;
+        p.gxyz1 = gxyz1 ? gxyz1 + (size_t)e0 * n * 3 : nullptr;
+        p.gxyz2 = gxyz2 ? gxyz2 + (size_t)e0 * m * 3 : nullptr;
+        p.w1 = w1; p.w2 = w2; p.zero_loss = (e0 == 0);
         nn_fwd_kernel<<<(unsigned)(pl.warps / kWarps), kWarps * 32, 0, st>>>(p);
         PNAE_CUDA_OK(cudaGetLastError());
-        {
-            const long long groups = (long long)p.be * ((long long)n + m);
-            const long long want_blocks = (groups * kFinLanes + kFinThreads - 1) / kFinThreads;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)min(want_blocks, (long long)sms * 24));
-            cfg.blockDim = dim3(kFinThreads);
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency overlaps the sweep's tail
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel, p));
-        }
+        const long long groups = (long long)p.be * ((long long)n + m);
+        const long long want_blocks = (groups * kFinLanes + kFinThreads - 1) / kFinThreads;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)min(want_blocks, (long long)sms * 24));
+        cfg.blockDim = dim3(kFinThreads);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency overlaps the sweep's tail
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (loss != nullptr) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true>, p));
+        else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false>, p));
     }
     return PNAE_OK;
+}
+}  // namespace
+
+extern "C" int pnae_nn_distance_fwd(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                    float *dist1, int *idx1, float *dist2, int *idx2,
+                                    void *workspace, size_t workspace_bytes, void *stream)
+{
+    PNAE_REQUIRE(b >= 0 && n >= 1 && m >= 1, "nn_distance: need b>=0, n>=1, m>=1 (got b=%d n=%d m=%d)", b, n, m);
+    PNAE_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "nn_distance: NULL pointer");
+    if (b == 0) return PNAE_OK;
+    return launch_fwd("nn_distance", b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, nullptr, nullptr, nullptr, 0.f, 0.f,
+                      workspace, workspace_bytes, stream);
+}
+
+extern "C" int pnae_chamfer_loss_grad(int b, int n, const float *xyz1, int m, const float *xyz2, float w1, float w2,
+                                      float *loss, float *grad_xyz1, float *grad_xyz2,
+                                      float *dist1, int *idx1, float *dist2, int *idx2,
+                                      void *workspace, size_t workspace_bytes, void *stream)
+{
+    PNAE_REQUIRE(b >= 1 && n >= 1 && m >= 1, "chamfer_loss_grad: need b>=1, n>=1, m>=1 (got b=%d n=%d m=%d)", b, n, m);
+    PNAE_REQUIRE(xyz1 && xyz2 && loss && grad_xyz1 && grad_xyz2, "chamfer_loss_grad: NULL pointer");
+    PNAE_REQUIRE((dist1 != nullptr) == (idx1 != nullptr) && (dist2 != nullptr) == (idx2 != nullptr),
+                 "chamfer_loss_grad: dist/idx outputs go in pairs");
+    return launch_fwd("chamfer_loss_grad", b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, loss, grad_xyz1, grad_xyz2, w1, w2,
+                      workspace, workspace_bytes, stream);
 }
 
 extern "C" int pnae_nn_distance_bwd(int b, int n, const float *xyz1, int m, const float *xyz2,

@@ -96,6 +96,33 @@ def chamfer_loss(pred, label):
     return loss * 100, loss
 
 
+class _ChamferLossFused(torch.autograd.Function):
+    """loss*100 of models/model.py:77-83 through pnae_chamfer_loss_grad: forward and both gradients in the two
+    launches of the forward; backward only scales the stashed gradients by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, pred, label):
+        from . import ops
+        b, n, _ = pred.shape
+        m = label.shape[1]
+        loss, g1, g2 = ops.chamfer_loss_grad(pred, label, 100.0 / (b * n), 100.0 / (b * m))
+        ctx.save_for_backward(g1, g2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        return (g1 * grad_loss if ctx.needs_input_grad[0] else None), (g2 * grad_loss if ctx.needs_input_grad[1] else None)
+
+
+def chamfer_loss_fused(pred, label):
+    """Same value and gradients as chamfer_loss(pred, label)[0] (requires n == m like the reference's
+    reduce_mean(dists_forward + dists_backward)), one op instead of two, no dist/idx tensors."""
+    assert pred.shape[1] == label.shape[1]
+    loss = _ChamferLossFused.apply(pred, label)
+    return loss, loss.detach() / 100
+
+
 def emd_loss(pred, label):
     """models/model_emd.py:79-89 -> (mean match_cost, pcloss); Chamfer is still evaluated, as in the reference"""
     d_fwd, _, d_bwd, _ = tf_nndistance.nn_distance(pred, label)

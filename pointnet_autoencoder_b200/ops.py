@@ -109,6 +109,22 @@ def nn_distance_bwd(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
     return o1, o2
 
 
+def chamfer_loss_grad(xyz1, xyz2, w1, w2):
+    """Fused: loss = w1*sum(dist1) + w2*sum(dist2) -> (loss (), grad_xyz1 (B,N,3), grad_xyz2 (B,M,3)); two launches"""
+    xyz1, xyz2, b, n, m = _check_pair("NnDistance", xyz1, xyz2, "nn")
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        g1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        g2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
+        ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.pnae_chamfer_loss_grad(b, n, _p(xyz1), m, _p(xyz2), float(w1), float(w2), _p(loss), _p(g1), _p(g2),
+                                              None, None, None, None, _p(ws), wsb, _stream(xyz1)))
+    return loss, g1, g2
+
+
 # ---------------------------------------------------------------------------
 # approximate EMD
 # ---------------------------------------------------------------------------

@@ -99,6 +99,24 @@ def test_chamfer_graph_step_equals_eager_calls():
     assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
 
 
+@pytest.mark.parametrize("b,n", [(2, 512), (3, 777), (32, 2048)])
+def test_fused_chamfer_loss_grad_equals_two_op_path(b, n):
+    from pointnet_autoencoder_b200 import models
+    label, pred = synthetic.s_chair(b, n)
+    lab = cu(label)
+    p_a = cu(pred).requires_grad_(True); p_b = cu(pred).requires_grad_(True)
+    la, _ = models.chamfer_loss(p_a, lab)            # nn_distance + nn_distance_grad (3 launches)
+    lb, _ = models.chamfer_loss_fused(p_b, lab)      # pnae_chamfer_loss_grad (2 launches)
+    (la * 1.7).backward(); (lb * 1.7).backward()
+    assert abs(la.item() - lb.item()) <= 2e-6 * abs(la.item())
+    close_scaled(p_b.grad.cpu().numpy(), p_a.grad.cpu().numpy(), 1e-5, "grad")
+    # and against the oracle
+    _, oi1, _, oi2 = O.nn_distance(pred, label)
+    g = np.full((b, n), 1.7 * 100.0 / (b * n), np.float32)
+    o1, _ = O.nn_distance_grad(pred, label, g, oi1, g, oi2)
+    close_scaled(p_b.grad.cpu().numpy(), o1, 1e-5, "grad vs oracle")
+
+
 def test_host_pipeline_matches_eager():
     from pointnet_autoencoder_b200 import host_api
     b, n, m = 2, 300, 200

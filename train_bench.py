@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (train.py default 32)")
     ap.add_argument("--unfused-encoder", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--two-op-loss", action="store_true", help="Chamfer loss through nn_distance + nn_distance_grad instead of the fused entry point")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--tf32", action="store_true", help="let the LIBRARY GEMMs/convs (decoder, encoder layers 1-4) use TF32 tensor cores")
     args = ap.parse_args()
@@ -89,7 +90,7 @@ def main():
         model = models.AutoEncoderUpconv(fused_encoder=not args.unfused_encoder).to(dev)
     else:
         model = models.AutoEncoderFC(num_point=n, fused_encoder=not args.unfused_encoder).to(dev)
-    loss_fn = models.emd_loss if args.model == "emd" else models.chamfer_loss
+    loss_fn = models.emd_loss if args.model == "emd" else (models.chamfer_loss if args.two_op_loss else models.chamfer_loss_fused)
     bucket = parallel.GradBucket(model.parameters())
     use_graph = not args.no_graph
     lr_t = torch.tensor(1e-3, device=dev)                  # tensor LR: the schedule can change it without re-capturing

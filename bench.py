@@ -30,7 +30,7 @@ B, N, M = 32, 2048, 2048
 METRIC = "nn_distance_fwd_grad_throughput"
 UNIT = "Gpairs/s"            # unordered (xyz1 point, xyz2 point) pairs: B*N*M per step
 FLOP_PER_PAIR = 16           # algorithmic: 2 directed evaluations x 8 FLOP (tf_nndistance_g.cu:25-28)
-RING = 64                    # distinct batches cycled through, so the working set exceeds the 126 MB L2
+RING = 128                   # distinct batches cycled through: 201 MB of inputs, larger than the 126 MB L2
 
 
 def make_inputs(b, n, m, ring, seed=100):

@@ -22,6 +22,8 @@
 //    candidates with the same arithmetic to emit the exact first argmin.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "pnae_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -69,7 +71,8 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
 }
 
 // warp that owns unit u under the span formula above
-__device__ __forceinline__ long long owner_of(long long u, long long warps, long long units)
+template <typename T>
+__device__ __forceinline__ T owner_of(T u, T warps, T units)
 {
     return ((u + 1) * warps - 1) / units;
 }
@@ -154,7 +157,7 @@ nn_fwd_kernel(const FwdParams p)
         const long long first = ((long long)held_e * p.nrb + held_rb) * p.nch;      // first unit of the row block
         // rank of this warp among the warps whose spans touch the row block: consecutive warps when every
         // warp has work (units >= warps), one warp per unit otherwise -- the smaller of the two counts
-        const int slot = (int)min(wid - owner_of(first, p.warps, p.units), held_u0 - first);
+        const int slot = (int)min(wid - owner_of<long long>(first, p.warps, p.units), held_u0 - first);
         u64 *rk = p.rowkeys + ((((size_t)held_e * p.nrb + held_rb) * p.nslot + slot) * kRowsPerBlock) + lane * kR;
 #pragma unroll
         for (int r = 0; r < kR; r++) rk[r] = ((u64)__float_as_uint(best[r]) << 32) | (unsigned)tag[r];
@@ -257,7 +260,9 @@ constexpr int kFinThreads = 256;
 //   d/d a_j = 2 w (a_j - c_nn(j)),   d/d c_nn(j) = -2 w (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148 with
 // grad_dist == w), so the Chamfer loss of models/model.py:80-83 needs no separate gradient launch and no dist/idx
 // round trip.  dist/idx outputs are optional on this path.
-template <bool FUSED>
+// IT: index type of the point / unit arithmetic.  unsigned when every product below fits 32 bits (the launcher
+// checks), which keeps the three divisions per point cheap; long long otherwise.
+template <bool FUSED, typename IT>
 __global__ void __launch_bounds__(kFinThreads, 4)
 nn_finalize_kernel(const FwdParams p)
 {
@@ -265,20 +270,24 @@ nn_finalize_kernel(const FwdParams p)
     const int sub = threadIdx.x & (kFinLanes - 1);
     // shuffles stay inside one point's lane group: a warp whose points straddle the xyz1/xyz2 boundary of an
     // element (n not a multiple of 32/kFinLanes) takes both branches below, so a full-warp mask would be divergent
-    const unsigned gmask = ((1u << kFinLanes) - 1u) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
-    const long long per_e = (long long)p.n + p.m;
-    const long long total = (long long)p.be * per_e;
+    const unsigned gmask = (unsigned)((1ull << kFinLanes) - 1ull) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
+    const IT per_e = (IT)p.n + (IT)p.m;
+    const IT total = (IT)p.be * per_e;
+    const IT W = (IT)p.warps, U = (IT)p.units;
     constexpr int kPtsPerWarp = 32 / kFinLanes;
-    const long long warp_id = ((long long)blockIdx.x * kFinThreads + threadIdx.x) >> 5;
-    const long long n_warps = (long long)gridDim.x * kFinThreads >> 5;
+    const IT warp_id = (IT)((blockIdx.x * (unsigned)kFinThreads + threadIdx.x) >> 5);
+    const IT n_warps = (IT)((gridDim.x * (unsigned)kFinThreads) >> 5);
+    // wide candidate loads need the element bases 16-byte (xyz2) / 8-byte (xyz1) aligned
+    const bool vec2 = (reinterpret_cast<size_t>(p.xyz2) & 15) == 0 && (p.m & 3) == 0;
+    const bool vec1 = (reinterpret_cast<size_t>(p.xyz1) & 7) == 0 && (p.n & 1) == 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // launched with programmatic stream serialization
     asm volatile("griddepcontrol.launch_dependents;");        // the gradient kernel may queue up behind us the same way
-    for (long long base = warp_id * kPtsPerWarp; base < total; base += n_warps * kPtsPerWarp) {   // warp-uniform trip count
-        const long long pt = base + (threadIdx.x & 31) / kFinLanes;
+    for (IT base = warp_id * kPtsPerWarp; base < total; base += n_warps * kPtsPerWarp) {   // warp-uniform trip count
+        const IT pt = base + (threadIdx.x & 31) / kFinLanes;
         const bool live = pt < total;
-        const long long q = live ? pt : total - 1;
+        const IT q = live ? pt : total - 1;
         const int e = (int)(q / per_e);
-        const int r = (int)(q - (long long)e * per_e);
+        const int r = (int)(q - (IT)e * per_e);
         const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
         const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
         if (r < p.n) {
@@ -286,9 +295,8 @@ nn_finalize_kernel(const FwdParams p)
             const int j = r;
             const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
             const int rb = j / kRowsPerBlock;
-            const long long first = ((long long)e * p.nrb + rb) * p.nch;
-            const int nsl = (int)min(owner_of(first + p.nch - 1, p.warps, p.units) - owner_of(first, p.warps, p.units) + 1,
-                                     (long long)p.nch);     // see flush_rows
+            const IT first = ((IT)e * p.nrb + rb) * p.nch;
+            const int nsl = (int)min(owner_of<IT>(first + p.nch - 1, W, U) - owner_of<IT>(first, W, U) + 1, (IT)p.nch);   // see flush_rows
             const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
             u64 key = ~0ull;       // (min bits, chunk): u64 order = lower distance, then lower chunk
             for (int sl = sub; sl < nsl; sl += 8 * kFinLanes) {
@@ -303,16 +311,25 @@ nn_finalize_kernel(const FwdParams p)
             const float want = __uint_as_float((unsigned)(key >> 32));
             const int k0 = (int)(unsigned)key * kChunk;
             constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
-            float cx[kPer], cy[kPer], cz[kPer];
+            float cf[kPer * 3];
+            if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
+                const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
 #pragma unroll
-            for (int c = 0; c < kPer; c++) {
-                const int k = min(k0 + sub * kPer + c, p.m - 1);
-                cx[c] = __ldg(p2 + k * 3); cy[c] = __ldg(p2 + k * 3 + 1); cz[c] = __ldg(p2 + k * 3 + 2);
+                for (int c = 0; c < kPer * 3 / 4; c++) {
+                    const float4 v = __ldg(src + c);
+                    cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kPer; c++) {
+                    const int k = min(k0 + sub * kPer + c, p.m - 1);
+                    cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
+                }
             }
             int found = 0x7fffffff;
 #pragma unroll
             for (int c = kPer - 1; c >= 0; c--)
-                if (pnae_sqdist(cx[c] - x, cy[c] - y, cz[c] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
+                if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
 #pragma unroll
             for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
             if (live && sub == 0) {
@@ -358,13 +375,25 @@ nn_finalize_kernel(const FwdParams p)
             const float want = __uint_as_float((unsigned)(key >> 32));
             const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
             constexpr int kPer = kR / kFinLanes;
+            float cf[kPer * 3];
+            if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
+                const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
+#pragma unroll
+                for (int c = 0; c < kPer * 3 / 2; c++) {
+                    const float2 v = __ldg(src + c);
+                    cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kPer; c++) {
+                    const int j = min(j0 + sub * kPer + c, p.n - 1);
+                    cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
+                }
+            }
             int found = 0x7fffffff;
 #pragma unroll
-            for (int c = kPer - 1; c >= 0; c--) {
-                const int j = min(j0 + sub * kPer + c, p.n - 1);
-                const float d = pnae_sqdist(x - __ldg(p1 + j * 3), y - __ldg(p1 + j * 3 + 1), z - __ldg(p1 + j * 3 + 2));
-                if (d == want) found = j;
-            }
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
 #pragma unroll
             for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
             if (live && sub == 0) {
@@ -386,8 +415,16 @@ nn_finalize_kernel(const FwdParams p)
         }
     }
     if (FUSED) {
+        __shared__ float s_loss[kFinThreads / 32];
         loss_acc = warp_sum(loss_acc);
-        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(p.loss, loss_acc);
+        if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = loss_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kFinThreads / 32; w++) t += s_loss[w];
+            if (t != 0.f) atomicAdd(p.loss, t);
+        }
     }
 }
 
@@ -521,8 +558,16 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (loss != nullptr) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true>, p));
-        else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false>, p));
+        // 32-bit index arithmetic whenever the point count and the span formula's (u+1)*warps fit
+        static const bool force64 = getenv("PNAE_NN_INDEX64") != nullptr;     // test hook for the wide path
+        const bool small = !force64 && groups < (1ll << 31) && (p.units + 1) * p.warps < (1ll << 32);
+        if (loss != nullptr) {
+            if (small) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true, unsigned>, p));
+            else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true, long long>, p));
+        } else {
+            if (small) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false, unsigned>, p));
+            else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false, long long>, p));
+        }
     }
     return PNAE_OK;
 }

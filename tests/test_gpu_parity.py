@@ -99,6 +99,26 @@ def test_chamfer_graph_step_equals_eager_calls():
     assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
 
 
+def test_finalize_wide_index_path_matches_oracle():
+    """The finalize kernel has a 64-bit index instantiation for launches whose point / unit counts overflow
+    32 bits; PNAE_NN_INDEX64 forces it at a size the oracle can check (separate process: the switch is read once)."""
+    import os, subprocess, sys, tempfile
+    x1, x2 = synthetic.s_randn(3, 333, 517, seed=21)
+    od1, oi1, od2, oi2 = O.nn_distance(x1, x2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "o.npz")
+        code = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+                "from pointnet_autoencoder_b200 import ops, synthetic\n"
+                "x1, x2 = synthetic.s_randn(3, 333, 517, seed=21)\n"
+                "r = ops.nn_distance_fwd(torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda())\n"
+                "np.savez(%r, *[t.cpu().numpy() for t in r])\n") % (root, out)
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, PNAE_NN_INDEX64="1"), timeout=600)
+        got = np.load(out)
+        for k, ref in zip(("arr_0", "arr_1", "arr_2", "arr_3"), (od1, oi1, od2, oi2)):
+            assert np.array_equal(got[k], ref), k
+
+
 @pytest.mark.parametrize("b,n", [(2, 512), (3, 777), (32, 2048)])
 def test_fused_chamfer_loss_grad_equals_two_op_path(b, n):
     from pointnet_autoencoder_b200 import models

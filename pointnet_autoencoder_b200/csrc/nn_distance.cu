@@ -47,7 +47,9 @@ struct FwdParams {
     int be;            // elements in this launch
     int n, m;
     int nrb, nch;      // row blocks / column chunks per element
-    int nslot;         // row-partial slots per row block (max warps whose spans touch one row block)
+    int nslot;         // row-partial slots per row block in the workspace layout (bound for any launch of the call)
+    int nsl;           // slots in use in THIS launch: spans touching one row block <= nsl <= nslot; slots the sweep
+                       // does not reach are filled with +inf keys, so the finalize reads nsl slots unconditionally
     long long units;   // be * nrb * nch
     long long warps;   // sweep grid size in warps: the span of warp w is [w*units/warps, (w+1)*units/warps)
     const float *xyz1, *xyz2;
@@ -60,6 +62,7 @@ struct FwdParams {
     float *gxyz1, *gxyz2;   // (be,n,3), (be,m,3): d loss / d xyz, zeroed by the sweep, accumulated by the finalize
     float w1, w2;
     int zero_loss;     // this launch is the first chunk of the call: it also zeroes *loss
+    int small;         // (units + 1) * warps and the point count fit 32 bits: cheap unsigned index arithmetic
 };
 
 // three-input minimum (FMNMX3); NaN operands are ignored like fminf
@@ -77,6 +80,20 @@ __device__ __forceinline__ T owner_of(T u, T warps, T units)
     return ((u + 1) * warps - 1) / units;
 }
 
+// explicit 32-bit shared-memory addressing for the sweep's inner loop (one base register, immediate offsets)
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ float4 lds128(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128_if(int pred, unsigned addr, unsigned x, unsigned y, unsigned z, unsigned w)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(pred) : "memory");
+}
+
 // cp.async (LDGSTS) helpers: 4-byte granularity because points are 12-byte xyz triples
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 {
@@ -86,27 +103,44 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // asynchronous copy of one chunk's 32 columns into float4 slots (w unused) and, on a row-block
-// change, of the block's 256 rows as flat xyz floats
+// change, of the block's 256 rows as flat xyz floats.  Interior chunks / row blocks are contiguous
+// in memory (96 / 768 floats): one base address, immediate offsets.  Only the last, partial chunk or
+// block of an element clamps its indices (duplicates of the last point never change a minimum).
 __device__ __forceinline__ void prefetch_unit(const FwdParams &p, int e, int rb, int ch, float *srow, float4 *scol,
                                               bool with_rows)
 {
     const int lane = threadIdx.x & 31;
     const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
     const int col0 = ch * kChunk;
+    if (col0 + kChunk <= p.m) {
+        const float *src = p2 + (size_t)col0 * 3 + lane;
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int f = lane + 32 * i, c = f / 3;
-        const int k = min(col0 + c, p.m - 1);              // clamped duplicates never change a minimum
-        cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), p2 + (size_t)k * 3 + (f - c * 3));
+        for (int i = 0; i < 3; i++) {
+            const int f = lane + 32 * i, c = f / 3;
+            cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), src + 32 * i);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int f = lane + 32 * i, c = f / 3;
+            const int k = min(col0 + c, p.m - 1);
+            cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), p2 + (size_t)k * 3 + (f - c * 3));
+        }
     }
     if (with_rows) {
         const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
         const int row0 = rb * kRowsPerBlock;
+        if (row0 + kRowsPerBlock <= p.n) {
+            const float *src = p1 + (size_t)row0 * 3 + lane;
 #pragma unroll
-        for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) {
-            const int f = lane + 32 * i, r = f / 3;
-            const int j = min(row0 + r, p.n - 1);
-            cp_async4(srow + f, p1 + (size_t)j * 3 + (f - r * 3));
+            for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) cp_async4(srow + lane + 32 * i, src + 32 * i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) {
+                const int f = lane + 32 * i, r = f / 3;
+                const int j = min(row0 + r, p.n - 1);
+                cp_async4(srow + f, p1 + (size_t)j * 3 + (f - r * 3));
+            }
         }
     }
     cp_async_commit();
@@ -116,7 +150,7 @@ __device__ __forceinline__ void prefetch_unit(const FwdParams &p, int e, int rb,
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 nn_fwd_kernel(const FwdParams p)
 {
-    __shared__ __align__(16) float4 scol_all[kWarps][2][kChunk];
+    __shared__ __align__(16) float4 scol_all[kWarps][2][kChunk + 1];   // +1: the loop's look-ahead load of the last group lands here
     __shared__ __align__(16) float srow_all[kWarps][kRowsPerBlock * 3];
     __shared__ __align__(16) u64 skey_all[kWarps][kChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,34 +167,58 @@ nn_fwd_kernel(const FwdParams p)
         if (tid == 0 && p.zero_loss) *p.loss = 0.f;
     }
     const long long wid = (long long)blockIdx.x * kWarps + warp;
-    long long u = wid * p.units / p.warps;
-    const long long uend = (wid + 1) * p.units / p.warps;
-    if (u >= uend) return;
-
     const int per_e = p.nrb * p.nch;
-    auto decode = [&](long long t, int &e, int &rb, int &ch) {
-        e = (int)(t / per_e);
-        const int r = (int)(t - (long long)e * per_e);
-        rb = r / p.nch;          // chunk fastest: a span stays inside one row block as long as possible
+    long long u, uend;
+    int e, rb, ch;
+    // span [u, uend) of this warp and the (element, row block, chunk) of its first unit; chunk fastest, so a
+    // span stays inside one row block as long as possible
+    if (p.small) {
+        const unsigned w = (unsigned)wid, W = (unsigned)p.warps, U = (unsigned)p.units;
+        const unsigned u0 = w * U / W;
+        u = u0; uend = (w + 1) * U / W;
+        e = (int)(u0 / (unsigned)per_e);
+        const unsigned r = u0 - (unsigned)e * (unsigned)per_e;
+        rb = (int)(r / (unsigned)p.nch);
+        ch = (int)(r - (unsigned)rb * (unsigned)p.nch);
+    } else {
+        u = wid * p.units / p.warps; uend = (wid + 1) * p.units / p.warps;
+        e = (int)(u / per_e);
+        const int r = (int)(u - (long long)e * per_e);
+        rb = r / p.nch;
         ch = r - rb * p.nch;
-    };
+    }
+    if (u >= uend) return;
 
     float rx[kR], ry[kR], rz[kR], best[kR], snap[kR];
     int tag[kR];
-    int e, rb, ch, held_e = -1, held_rb = -1, buf = 0;
+    int held_e = -1, held_rb = -1, buf = 0;
     long long held_u0 = 0;        // first unit this warp swept in the row block it holds
-    decode(u, e, rb, ch);
+    u64 *ckrow = nullptr;         // column keys of the row block it holds
     prefetch_unit(p, e, rb, ch, srow, scol_all[warp][buf], true);
 
     // store this warp's partial row keys of the row block it is leaving
     auto flush_rows = [&]() {
         const long long first = ((long long)held_e * p.nrb + held_rb) * p.nch;      // first unit of the row block
+        auto owner = [&](long long t) {
+            return p.small ? (long long)owner_of<unsigned>((unsigned)t, (unsigned)p.warps, (unsigned)p.units)
+                           : owner_of<long long>(t, p.warps, p.units);
+        };
         // rank of this warp among the warps whose spans touch the row block: consecutive warps when every
         // warp has work (units >= warps), one warp per unit otherwise -- the smaller of the two counts
-        const int slot = (int)min(wid - owner_of<long long>(first, p.warps, p.units), held_u0 - first);
-        u64 *rk = p.rowkeys + ((((size_t)held_e * p.nrb + held_rb) * p.nslot + slot) * kRowsPerBlock) + lane * kR;
+        const long long own = owner(first);
+        const int slot = (int)min(wid - own, held_u0 - first);
+        u64 *rk0 = p.rowkeys + (((size_t)held_e * p.nrb + held_rb) * p.nslot) * kRowsPerBlock + lane * kR;
+        u64 *rk = rk0 + (size_t)slot * kRowsPerBlock;
 #pragma unroll
         for (int r = 0; r < kR; r++) rk[r] = ((u64)__float_as_uint(best[r]) << 32) | (unsigned)tag[r];
+        if (held_u0 == first) {
+            // the warp that swept the block's first unit also pads the slots no span reaches
+            const int used = (int)min(owner(first + p.nch - 1) - own + 1, (long long)p.nch);
+            for (int sl = used; sl < p.nsl; sl++) {
+#pragma unroll
+                for (int r = 0; r < kR; r++) rk0[(size_t)sl * kRowsPerBlock + r] = ~0ull;
+            }
+        }
     };
 
     for (; u < uend; u++) {
@@ -182,6 +240,7 @@ nn_fwd_kernel(const FwdParams p)
                 tag[r] = 0;
             }
             held_e = e; held_rb = rb; held_u0 = u;
+            ckrow = p.colkeys + ((size_t)e * p.nrb + rb) * p.m;
         }
         __syncwarp();      // every lane has its rows in registers: the row buffer may be refilled
         // successor unit without divisions: chunk fastest, then row block, then element
@@ -190,10 +249,13 @@ nn_fwd_kernel(const FwdParams p)
         if (u + 1 < uend) prefetch_unit(p, e2, rb2, ch2, srow, scol_all[warp][buf ^ 1], ch2 == 0);
 
         // ---- 256 rows x 32 columns
-        const float4 *scol = scol_all[warp][buf];
         u64 *skey = skey_all[warp];
-        float4 qn = scol[0];
-        for (int c0 = 0; c0 < kChunk; c0 += kGroup) {
+        unsigned ca = smem_u32(scol_all[warp][buf]), ka = smem_u32(skey);
+        const unsigned cend = ca + kChunk * (unsigned)sizeof(float4);
+        const int lane0 = lane == 0;
+        float4 qn = lds128(ca);
+#pragma unroll 1
+        do {
             // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
             // independent chains, issued back to back so their fixed latencies overlap
             unsigned bits[kGroup];
@@ -202,8 +264,8 @@ nn_fwd_kernel(const FwdParams p)
                 // two columns at a time so the minima can use the three-input FMNMX3 (two mins per issue slot;
                 // measured on B200 at 1.15 cycles per min against 1.65 for the two-input form)
                 const float4 q0 = qn;
-                const float4 q1 = scol[(c0 + g + 1) & (kChunk - 1)];
-                qn = scol[(c0 + g + 2) & (kChunk - 1)];  // next pair's first record is in flight during this pair's math
+                const float4 q1 = lds128(ca + (g + 1) * (unsigned)sizeof(float4));
+                qn = lds128(ca + (g + 2) * (unsigned)sizeof(float4));   // next pair's first record is in flight during this pair's math
                 float d0[kR], d1[kR];
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
@@ -221,13 +283,12 @@ nn_fwd_kernel(const FwdParams p)
             for (int g = 0; g < kGroup; g++) mn[g] = __reduce_min_sync(0xffffffffu, bits[g]);
 #pragma unroll
             for (int g = 0; g < kGroup; g++) who[g] = __ballot_sync(0xffffffffu, bits[g] == mn[g]);
-            if (lane == 0) {
-#pragma unroll
-                for (int g = 0; g < kGroup; g += 2)
-                    *reinterpret_cast<ulonglong2 *>(skey + c0 + g) =
-                        make_ulonglong2(((u64)mn[g] << 32) | who[g], ((u64)mn[g + 1] << 32) | who[g + 1]);
-            }
-        }
+            static_assert(kGroup == 4, "two 16-byte key stores per group");
+            sts128_if(lane0, ka, who[0], mn[0], who[1], mn[1]);          // u64 key = min bits << 32 | ballot
+            sts128_if(lane0, ka + 16, who[2], mn[2], who[3], mn[3]);
+            ca += kGroup * (unsigned)sizeof(float4);
+            ka += kGroup * (unsigned)sizeof(u64);
+        } while (ca != cend);
         __syncwarp();
         const u64 mykey = skey[lane];                    // lane c carries the key of column c of this chunk
         __syncwarp();
@@ -238,7 +299,7 @@ nn_fwd_kernel(const FwdParams p)
             snap[r] = best[r];
         }
         const int k = ch * kChunk + lane;
-        if (k < p.m) p.colkeys[((size_t)e * p.nrb + rb) * p.m + k] = mykey;
+        if (k < p.m) ckrow[k] = mykey;
         buf ^= 1;
         e = e2; rb = rb2; ch = ch2;
     }
@@ -260,9 +321,9 @@ constexpr int kFinThreads = 256;
 //   d/d a_j = 2 w (a_j - c_nn(j)),   d/d c_nn(j) = -2 w (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148 with
 // grad_dist == w), so the Chamfer loss of models/model.py:80-83 needs no separate gradient launch and no dist/idx
 // round trip.  dist/idx outputs are optional on this path.
-// IT: index type of the point / unit arithmetic.  unsigned when every product below fits 32 bits (the launcher
-// checks), which keeps the three divisions per point cheap; long long otherwise.
-template <bool FUSED, typename IT>
+// Grid: x = blocks of kFinThreads/kFinLanes points of one element (its n points of xyz1, then its m of xyz2),
+// y = element: no divisions anywhere.
+template <bool FUSED>
 __global__ void __launch_bounds__(kFinThreads, 4)
 nn_finalize_kernel(const FwdParams p)
 {
@@ -271,146 +332,136 @@ nn_finalize_kernel(const FwdParams p)
     // shuffles stay inside one point's lane group: a warp whose points straddle the xyz1/xyz2 boundary of an
     // element (n not a multiple of 32/kFinLanes) takes both branches below, so a full-warp mask would be divergent
     const unsigned gmask = (unsigned)((1ull << kFinLanes) - 1ull) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
-    const IT per_e = (IT)p.n + (IT)p.m;
-    const IT total = (IT)p.be * per_e;
-    const IT W = (IT)p.warps, U = (IT)p.units;
-    constexpr int kPtsPerWarp = 32 / kFinLanes;
-    const IT warp_id = (IT)((blockIdx.x * (unsigned)kFinThreads + threadIdx.x) >> 5);
-    const IT n_warps = (IT)((gridDim.x * (unsigned)kFinThreads) >> 5);
+    const int per_e = p.n + p.m;
+    const int e = blockIdx.y;
+    const int pt = (int)(blockIdx.x * (unsigned)(kFinThreads / kFinLanes) + threadIdx.x / kFinLanes);
+    const bool live = pt < per_e;
+    const int r = live ? pt : per_e - 1;
+    const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
+    const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
     // wide candidate loads need the element bases 16-byte (xyz2) / 8-byte (xyz1) aligned
     const bool vec2 = (reinterpret_cast<size_t>(p.xyz2) & 15) == 0 && (p.m & 3) == 0;
     const bool vec1 = (reinterpret_cast<size_t>(p.xyz1) & 7) == 0 && (p.n & 1) == 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // launched with programmatic stream serialization
     asm volatile("griddepcontrol.launch_dependents;");        // the gradient kernel may queue up behind us the same way
-    for (IT base = warp_id * kPtsPerWarp; base < total; base += n_warps * kPtsPerWarp) {   // warp-uniform trip count
-        const IT pt = base + (threadIdx.x & 31) / kFinLanes;
-        const bool live = pt < total;
-        const IT q = live ? pt : total - 1;
-        const int e = (int)(q / per_e);
-        const int r = (int)(q - (IT)e * per_e);
-        const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
-        const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
-        if (r < p.n) {
-            // point j of xyz1 -> dist1 / idx1
-            const int j = r;
-            const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
-            const int rb = j / kRowsPerBlock;
-            const IT first = ((IT)e * p.nrb + rb) * p.nch;
-            const int nsl = (int)min(owner_of<IT>(first + p.nch - 1, W, U) - owner_of<IT>(first, W, U) + 1, (IT)p.nch);   // see flush_rows
-            const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
-            u64 key = ~0ull;       // (min bits, chunk): u64 order = lower distance, then lower chunk
-            for (int sl = sub; sl < nsl; sl += 8 * kFinLanes) {
-                u64 v[8];
+    if (r < p.n) {
+        // point j of xyz1 -> dist1 / idx1
+        const int j = r;
+        const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
+        const int rb = j / kRowsPerBlock;
+        const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
+        u64 key = ~0ull;       // (min bits, chunk): u64 order = lower distance, then lower chunk
+        for (int sl = sub; sl < p.nsl; sl += 4 * kFinLanes) {
+            u64 v[4];
 #pragma unroll
-                for (int t = 0; t < 8; t++) v[t] = (sl + t * kFinLanes < nsl) ? __ldcg(rk + (size_t)(sl + t * kFinLanes) * kRowsPerBlock) : ~0ull;
+            for (int t = 0; t < 4; t++) v[t] = (sl + t * kFinLanes < p.nsl) ? __ldcg(rk + (size_t)(sl + t * kFinLanes) * kRowsPerBlock) : ~0ull;
 #pragma unroll
-                for (int t = 0; t < 8; t++) key = min(key, v[t]);
-            }
+            for (int t = 0; t < 4; t++) key = min(key, v[t]);
+        }
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
-            const float want = __uint_as_float((unsigned)(key >> 32));
-            const int k0 = (int)(unsigned)key * kChunk;
-            constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
-            float cf[kPer * 3];
-            if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
-                const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
+        for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
+        const float want = __uint_as_float((unsigned)(key >> 32));
+        const int k0 = (int)(unsigned)key * kChunk;
+        constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
+        float cf[kPer * 3];
+        if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
+            const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
 #pragma unroll
-                for (int c = 0; c < kPer * 3 / 4; c++) {
-                    const float4 v = __ldg(src + c);
-                    cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < kPer; c++) {
-                    const int k = min(k0 + sub * kPer + c, p.m - 1);
-                    cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
-                }
-            }
-            int found = 0x7fffffff;
-#pragma unroll
-            for (int c = kPer - 1; c >= 0; c--)
-                if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
-#pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
-            if (live && sub == 0) {
-                const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
-                if (p.dist1 != nullptr) {
-                    p.dist1[(size_t)e * p.n + j] = want;
-                    p.idx1[(size_t)e * p.n + j] = nn;
-                }
-                if (FUSED) {
-                    loss_acc = fmaf(p.w1, want, loss_acc);
-                    const float g = __fmul_rn(p.w1, 2.0f);
-                    float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
-                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
-                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
-                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
-                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
-                }
+            for (int c = 0; c < kPer * 3 / 4; c++) {
+                const float4 v = __ldg(src + c);
+                cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
             }
         } else {
-            // point k of xyz2 -> dist2 / idx2
-            const int k = r - p.n;
-            const float x = __ldg(p2 + k * 3), y = __ldg(p2 + k * 3 + 1), z = __ldg(p2 + k * 3 + 2);
-            const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
-            u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
-            unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
-            for (int rb = sub; rb < p.nrb; rb += 8 * kFinLanes) {
-                u64 v[8];
 #pragma unroll
-                for (int t = 0; t < 8; t++) v[t] = (rb + t * kFinLanes < p.nrb) ? __ldcg(ck + (size_t)(rb + t * kFinLanes) * p.m) : ~0ull;
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const u64 cand = (v[t] & 0xffffffff00000000ull) | (unsigned)(rb + t * kFinLanes);
-                    if (rb + t * kFinLanes < p.nrb && cand < key) { key = cand; who = (unsigned)v[t]; }
-                }
+            for (int c = 0; c < kPer; c++) {
+                const int k = min(k0 + sub * kPer + c, p.m - 1);
+                cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
             }
+        }
+        int found = 0x7fffffff;
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) {
-                const u64 k2 = __shfl_xor_sync(gmask, key, o);
-                const unsigned w2 = __shfl_xor_sync(gmask, who, o);
-                if (k2 < key) { key = k2; who = w2; }
+        for (int c = kPer - 1; c >= 0; c--)
+            if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
+#pragma unroll
+        for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+        if (live && sub == 0) {
+            const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
+            if (p.dist1 != nullptr) {
+                p.dist1[(size_t)e * p.n + j] = want;
+                p.idx1[(size_t)e * p.n + j] = nn;
             }
-            const int rbw = (int)(unsigned)key;
-            const float want = __uint_as_float((unsigned)(key >> 32));
-            const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
-            constexpr int kPer = kR / kFinLanes;
-            float cf[kPer * 3];
-            if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
-                const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
-#pragma unroll
-                for (int c = 0; c < kPer * 3 / 2; c++) {
-                    const float2 v = __ldg(src + c);
-                    cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < kPer; c++) {
-                    const int j = min(j0 + sub * kPer + c, p.n - 1);
-                    cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
-                }
+            if (FUSED) {
+                loss_acc = __fmul_rn(p.w1, want);
+                const float g = __fmul_rn(p.w1, 2.0f);
+                float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
+                const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
+                const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
+                atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
             }
-            int found = 0x7fffffff;
+        }
+    } else {
+        // point k of xyz2 -> dist2 / idx2
+        const int k = r - p.n;
+        const float x = __ldg(p2 + k * 3), y = __ldg(p2 + k * 3 + 1), z = __ldg(p2 + k * 3 + 2);
+        const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
+        u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
+        unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
+        for (int rb = sub; rb < p.nrb; rb += 4 * kFinLanes) {
+            u64 v[4];
 #pragma unroll
-            for (int c = kPer - 1; c >= 0; c--)
-                if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
+            for (int t = 0; t < 4; t++) v[t] = (rb + t * kFinLanes < p.nrb) ? __ldcg(ck + (size_t)(rb + t * kFinLanes) * p.m) : ~0ull;
 #pragma unroll
-            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
-            if (live && sub == 0) {
-                const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
-                if (p.dist2 != nullptr) {
-                    p.dist2[(size_t)e * p.m + k] = want;
-                    p.idx2[(size_t)e * p.m + k] = nn;
-                }
-                if (FUSED) {
-                    loss_acc = fmaf(p.w2, want, loss_acc);
-                    const float g = __fmul_rn(p.w2, 2.0f);
-                    float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
-                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
-                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
-                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
-                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
-                }
+            for (int t = 0; t < 4; t++) {
+                const u64 cand = (v[t] & 0xffffffff00000000ull) | (unsigned)(rb + t * kFinLanes);
+                if (rb + t * kFinLanes < p.nrb && cand < key) { key = cand; who = (unsigned)v[t]; }
+            }
+        }
+#pragma unroll
+        for (int o = kFinLanes / 2; o > 0; o >>= 1) {
+            const u64 k2 = __shfl_xor_sync(gmask, key, o);
+            const unsigned w2 = __shfl_xor_sync(gmask, who, o);
+            if (k2 < key) { key = k2; who = w2; }
+        }
+        const int rbw = (int)(unsigned)key;
+        const float want = __uint_as_float((unsigned)(key >> 32));
+        const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
+        constexpr int kPer = kR / kFinLanes;
+        float cf[kPer * 3];
+        if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
+            const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
+#pragma unroll
+            for (int c = 0; c < kPer * 3 / 2; c++) {
+                const float2 v = __ldg(src + c);
+                cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kPer; c++) {
+                const int j = min(j0 + sub * kPer + c, p.n - 1);
+                cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
+            }
+        }
+        int found = 0x7fffffff;
+#pragma unroll
+        for (int c = kPer - 1; c >= 0; c--)
+            if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
+#pragma unroll
+        for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+        if (live && sub == 0) {
+            const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
+            if (p.dist2 != nullptr) {
+                p.dist2[(size_t)e * p.m + k] = want;
+                p.idx2[(size_t)e * p.m + k] = nn;
+            }
+            if (FUSED) {
+                loss_acc = __fmul_rn(p.w2, want);
+                const float g = __fmul_rn(p.w2, 2.0f);
+                float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
+                const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
+                const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
+                atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
             }
         }
     }
@@ -447,7 +498,7 @@ FwdPlan make_plan(int b, int n, int m, int sms)
     pl.nslot = (int)min((long long)pl.nch, (pl.nch + min_span - 1) / min_span + 1);
     const size_t per_e = sizeof(u64) * ((size_t)pl.nrb * pl.nslot * kRowsPerBlock + (size_t)pl.nrb * m);
     const long long be = (long long)(kWsBudget / (per_e ? per_e : 1));
-    pl.be = (int)max(1ll, min((long long)b, be));
+    pl.be = (int)max(1ll, min(min((long long)b, be), 65535ll));   // the finalize grid carries the element in blockIdx.y
     pl.row_bytes = sizeof(u64) * (size_t)pl.be * pl.nrb * pl.nslot * kRowsPerBlock;
     pl.col_bytes = sizeof(u64) * (size_t)pl.be * pl.nrb * m;
     pl.total = pl.row_bytes + pl.col_bytes;
@@ -528,6 +579,7 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         return PNAE_ERR_WORKSPACE;
     }
     PNAE_REQUIRE(pnae_aligned(workspace, 8), "%s: workspace must be 8-byte aligned", op);
+    PNAE_REQUIRE((long long)n + m < (1ll << 31), "%s: n + m must be below 2^31 (got %d + %d)", op, n, m);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     for (int e0 = 0; e0 < b; e0 += pl.be) {
@@ -545,12 +597,18 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         p.gxyz1 = gxyz1 ? gxyz1 + (size_t)e0 * n * 3 : nullptr;
         p.gxyz2 = gxyz2 ? gxyz2 + (size_t)e0 * m * 3 : nullptr;
         p.w1 = w1; p.w2 = w2; p.zero_loss = (e0 == 0);
+        // 32-bit index arithmetic whenever the point count and the span formula's (u+1)*warps fit
+        static const bool force64 = getenv("PNAE_NN_INDEX64") != nullptr;     // test hook for the wide path
+        const long long groups = (long long)p.be * ((long long)n + m);
+        const bool small = !force64 && groups < (1ll << 31) && (p.units + 1) * p.warps < (1ll << 32);
+        p.small = small;
+        // slots one row block can need in this launch: its nch units meet at most ceil(nch / shortest span) + 1 spans
+        const long long span = p.units / p.warps;
+        p.nsl = span >= 1 ? (int)min((long long)pl.nslot, (pl.nch + span - 1) / span + 1) : pl.nslot;
         nn_fwd_kernel<<<(unsigned)(pl.warps / kWarps), kWarps * 32, 0, st>>>(p);
         PNAE_CUDA_OK(cudaGetLastError());
-        const long long groups = (long long)p.be * ((long long)n + m);
-        const long long want_blocks = (groups * kFinLanes + kFinThreads - 1) / kFinThreads;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)min(want_blocks, (long long)sms * 24));
+        cfg.gridDim = dim3((unsigned)((n + m + kFinThreads / kFinLanes - 1) / (kFinThreads / kFinLanes)), (unsigned)p.be);
         cfg.blockDim = dim3(kFinThreads);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -558,16 +616,8 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        // 32-bit index arithmetic whenever the point count and the span formula's (u+1)*warps fit
-        static const bool force64 = getenv("PNAE_NN_INDEX64") != nullptr;     // test hook for the wide path
-        const bool small = !force64 && groups < (1ll << 31) && (p.units + 1) * p.warps < (1ll << 32);
-        if (loss != nullptr) {
-            if (small) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true, unsigned>, p));
-            else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true, long long>, p));
-        } else {
-            if (small) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false, unsigned>, p));
-            else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false, long long>, p));
-        }
+        if (loss != nullptr) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true>, p));
+        else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false>, p));
     }
     return PNAE_OK;
 }

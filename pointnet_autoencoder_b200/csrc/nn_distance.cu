@@ -41,6 +41,10 @@ constexpr int kGroup = 4;             // columns whose cross-lane reductions are
 #define PNAE_NN_CTAS 4
 #endif
 constexpr int kCtasPerSm = PNAE_NN_CTAS;
+#ifndef PNAE_NN_UNROLL
+#define PNAE_NN_UNROLL 2
+#endif
+constexpr int kUnroll = PNAE_NN_UNROLL;   // column groups per trip of the sweep's inner loop
 constexpr size_t kWsBudget = 256ull << 20;
 
 struct FwdParams {
@@ -158,14 +162,6 @@ nn_fwd_kernel(const FwdParams p)
     // let the finalize launch become resident as SMs drain (it blocks in cudaGridDependencySynchronize
     // until every CTA of this grid has finished and flushed): its launch latency hides under the sweep's tail
     asm volatile("griddepcontrol.launch_dependents;");
-    if (p.gxyz1 != nullptr) {
-        // fused loss+gradient: the finalize accumulates into these with atomics, so clear them here (it cannot
-        // start touching them before this whole grid has finished)
-        const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-        for (long long i = tid; i < (long long)p.be * p.n * 3; i += nt) p.gxyz1[i] = 0.f;
-        for (long long i = tid; i < (long long)p.be * p.m * 3; i += nt) p.gxyz2[i] = 0.f;
-        if (tid == 0 && p.zero_loss) *p.loss = 0.f;
-    }
     const long long wid = (long long)blockIdx.x * kWarps + warp;
     const int per_e = p.nrb * p.nch;
     long long u, uend;
@@ -186,6 +182,17 @@ nn_fwd_kernel(const FwdParams p)
         const int r = (int)(u - (long long)e * per_e);
         rb = r / p.nch;
         ch = r - rb * p.nch;
+    }
+    // this grid is itself launched with programmatic stream serialization: everything above (parameters only)
+    // may run while the kernel before it drains; global memory may only be touched from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.gxyz1 != nullptr) {
+        // fused loss+gradient: the finalize accumulates into these with atomics, so clear them here (it cannot
+        // start touching them before this whole grid has finished)
+        const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+        for (long long i = tid; i < (long long)p.be * p.n * 3; i += nt) p.gxyz1[i] = 0.f;
+        for (long long i = tid; i < (long long)p.be * p.m * 3; i += nt) p.gxyz2[i] = 0.f;
+        if (tid == 0 && p.zero_loss) *p.loss = 0.f;
     }
     if (u >= uend) return;
 
@@ -254,7 +261,7 @@ nn_fwd_kernel(const FwdParams p)
         const unsigned cend = ca + kChunk * (unsigned)sizeof(float4);
         const int lane0 = lane == 0;
         float4 qn = lds128(ca);
-#pragma unroll 1
+#pragma unroll kUnroll
         do {
             // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
             // independent chains, issued back to back so their fixed latencies overlap
@@ -315,7 +322,14 @@ nn_fwd_kernel(const FwdParams p)
 #define PNAE_NN_FINLANES 4
 #endif
 constexpr int kFinLanes = PNAE_NN_FINLANES;
-constexpr int kFinThreads = 256;
+#ifndef PNAE_NN_FINTHREADS
+#define PNAE_NN_FINTHREADS 128
+#endif
+#ifndef PNAE_NN_FINOCC
+#define PNAE_NN_FINOCC 8
+#endif
+constexpr int kFinThreads = PNAE_NN_FINTHREADS;
+constexpr int kFinOcc = PNAE_NN_FINOCC;       // resident CTAs per SM the finalize is compiled for
 
 // FUSED: additionally accumulate loss = w1*sum(dist1) + w2*sum(dist2) and its gradient
 //   d/d a_j = 2 w (a_j - c_nn(j)),   d/d c_nn(j) = -2 w (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148 with
@@ -324,7 +338,7 @@ constexpr int kFinThreads = 256;
 // Grid: x = blocks of kFinThreads/kFinLanes points of one element (its n points of xyz1, then its m of xyz2),
 // y = element: no divisions anywhere.
 template <bool FUSED>
-__global__ void __launch_bounds__(kFinThreads, 4)
+__global__ void __launch_bounds__(kFinThreads, kFinOcc)
 nn_finalize_kernel(const FwdParams p)
 {
     float loss_acc = 0.f;
@@ -526,6 +540,7 @@ nn_bwd_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *
     const int cs = (int)cluster.num_blocks();
     const int nclusters = gridDim.x / cs;
     const int tid = (int)cluster.block_rank() * kBwdThreads + threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;");        // a following sweep may set itself up while this grid runs
     asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: idx comes from the kernel before
     const int stride = cs * kBwdThreads;
     for (int e = blockIdx.x / cs; e < b; e += nclusters) {
@@ -605,17 +620,18 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         // slots one row block can need in this launch: its nch units meet at most ceil(nch / shortest span) + 1 spans
         const long long span = p.units / p.warps;
         p.nsl = span >= 1 ? (int)min((long long)pl.nslot, (pl.nch + span - 1) / span + 1) : pl.nslot;
-        nn_fwd_kernel<<<(unsigned)(pl.warps / kWarps), kWarps * 32, 0, st>>>(p);
-        PNAE_CUDA_OK(cudaGetLastError());
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((n + m + kFinThreads / kFinLanes - 1) / (kFinThreads / kFinLanes)), (unsigned)p.be);
-        cfg.blockDim = dim3(kFinThreads);
-        cfg.stream = st;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency overlaps the sweep's tail
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency overlaps the previous kernel's tail
         attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(pl.warps / kWarps));
+        cfg.blockDim = dim3(kWarps * 32);
+        cfg.stream = st;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_fwd_kernel, p));
+        cfg.gridDim = dim3((unsigned)((n + m + kFinThreads / kFinLanes - 1) / (kFinThreads / kFinLanes)), (unsigned)p.be);
+        cfg.blockDim = dim3(kFinThreads);
         if (loss != nullptr) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true>, p));
         else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false>, p));
     }

@@ -33,7 +33,7 @@ for h, v in sorted(st, key=lambda x: -x[1])[:12]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", ":::%d" % (kidx + 1)] if kidx else ["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h2 = rows[1]; ix = {h: i for i, h in enumerate(h2)}
-data = [r for r in rows[2:] if len(r) == len(h2)]
+data = [r for r in rows[2:] if len(r) == len(h2) and r[ix["# Samples"]].isdigit()]
 tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
 print("hottest instructions (samples, %%, executed, dominant stalls):")
 cols = [c for c in h2 if c.startswith("stall_") and "Not Issued" not in c]

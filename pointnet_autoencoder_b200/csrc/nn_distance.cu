@@ -92,6 +92,16 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ u64 lds64(unsigned addr)
+{
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, unsigned x, unsigned y, unsigned z, unsigned w)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void sts128_if(int pred, unsigned addr, unsigned x, unsigned y, unsigned z, unsigned w)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
@@ -99,85 +109,95 @@ __device__ __forceinline__ void sts128_if(int pred, unsigned addr, unsigned x, u
 }
 
 // cp.async (LDGSTS) helpers: 4-byte granularity because points are 12-byte xyz triples
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gmem_src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// asynchronous copy of one chunk's 32 columns into float4 slots (w unused) and, on a row-block
-// change, of the block's 256 rows as flat xyz floats.  Interior chunks / row blocks are contiguous
-// in memory (96 / 768 floats): one base address, immediate offsets.  Only the last, partial chunk or
-// block of an element clamps its indices (duplicates of the last point never change a minimum).
-__device__ __forceinline__ void prefetch_unit(const FwdParams &p, int e, int rb, int ch, float *srow, float4 *scol,
-                                              bool with_rows)
+// Asynchronous copy of one chunk's 32 columns into float4 slots (w unused) at shared address scol_s.  An
+// interior chunk is 96 contiguous floats: one base address, immediate offsets.  Only the last, partial chunk
+// of an element clamps its indices (duplicates of the last point never change a minimum).
+__device__ __forceinline__ void prefetch_cols(const float *p2, int m, int ch, unsigned scol_s, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
     const int col0 = ch * kChunk;
-    if (col0 + kChunk <= p.m) {
+    if (col0 + kChunk <= m) {
         const float *src = p2 + (size_t)col0 * 3 + lane;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int f = lane + 32 * i, c = f / 3;
-            cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), src + 32 * i);
+            cp_async4(scol_s + c * 16 + (f - c * 3) * 4, src + 32 * i);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int f = lane + 32 * i, c = f / 3;
-            const int k = min(col0 + c, p.m - 1);
-            cp_async4(reinterpret_cast<float *>(scol + c) + (f - c * 3), p2 + (size_t)k * 3 + (f - c * 3));
+            const int k = min(col0 + c, m - 1);
+            cp_async4(scol_s + c * 16 + (f - c * 3) * 4, p2 + (size_t)k * 3 + (f - c * 3));
         }
     }
-    if (with_rows) {
-        const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
-        const int row0 = rb * kRowsPerBlock;
-        if (row0 + kRowsPerBlock <= p.n) {
-            const float *src = p1 + (size_t)row0 * 3 + lane;
-#pragma unroll
-            for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) cp_async4(srow + lane + 32 * i, src + 32 * i);
-        } else {
-#pragma unroll
-            for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) {
-                const int f = lane + 32 * i, r = f / 3;
-                const int j = min(row0 + r, p.n - 1);
-                cp_async4(srow + f, p1 + (size_t)j * 3 + (f - r * 3));
-            }
-        }
-    }
-    cp_async_commit();
 }
 
-// Sweep launch.  Each warp is an independent worker walking its span of units.
+// Same for the 256 rows of row block rb, as flat xyz floats (768 contiguous floats when the block is interior).
+__device__ __forceinline__ void prefetch_rows(const float *p1, int n, int rb, unsigned srow_s, int lane)
+{
+    const int row0 = rb * kRowsPerBlock;
+    if (row0 + kRowsPerBlock <= n) {
+        const float *src = p1 + (size_t)row0 * 3 + lane;
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) cp_async4(srow_s + (lane + 32 * i) * 4, src + 32 * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock * 3 / 32; i++) {
+            const int f = lane + 32 * i, r = f / 3;
+            const int j = min(row0 + r, n - 1);
+            cp_async4(srow_s + f * 4, p1 + (size_t)j * 3 + (f - r * 3));
+        }
+    }
+}
+
+// Sweep launch.  Each warp is an independent worker walking its span of units: an outer loop over the row
+// blocks the span touches (rows loaded to registers, partial row keys flushed on leaving), an inner loop over
+// the span's chunks inside that row block with no index arithmetic beyond a few running pointers.
+struct __align__(16) SweepSmem {                 // per warp
+    float4 col[2][kChunk + 1];                   // +1: the loop's look-ahead load of the last group lands there
+    float row[kRowsPerBlock * 3];
+    u64 key[kChunk];
+    float4 snap[kR / 4][32];                     // each lane's row minima as of the previous chunk boundary
+    int4 tag[kR / 4][32];                        // chunk in which each row's minimum last strictly decreased
+};
+
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 nn_fwd_kernel(const FwdParams p)
 {
-    __shared__ __align__(16) float4 scol_all[kWarps][2][kChunk + 1];   // +1: the loop's look-ahead load of the last group lands here
-    __shared__ __align__(16) float srow_all[kWarps][kRowsPerBlock * 3];
-    __shared__ __align__(16) u64 skey_all[kWarps][kChunk];
+    constexpr unsigned kColBuf = (kChunk + 1) * (unsigned)sizeof(float4);
+    constexpr unsigned kRowOff = 2 * kColBuf, kKeyOff = kRowOff + kRowsPerBlock * 12;
+    constexpr unsigned kSnapOff = kKeyOff + kChunk * 8, kTagOff = kSnapOff + kR * 32 * 4;
+    static_assert(kKeyOff % 16 == 0 && sizeof(SweepSmem) == kTagOff + kR * 32 * 4, "SweepSmem layout");
+    __shared__ SweepSmem smem_all[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *srow = srow_all[warp];
     // let the finalize launch become resident as SMs drain (it blocks in cudaGridDependencySynchronize
     // until every CTA of this grid has finished and flushed): its launch latency hides under the sweep's tail
     asm volatile("griddepcontrol.launch_dependents;");
-    const long long wid = (long long)blockIdx.x * kWarps + warp;
+    const unsigned sm_s = smem_u32(&smem_all[warp]);       // the one shared-memory base register of this warp
+    const int wid = blockIdx.x * kWarps + warp;
     const int per_e = p.nrb * p.nch;
-    long long u, uend;
+    int rem;                      // units left in this warp's span
     int e, rb, ch;
     // span [u, uend) of this warp and the (element, row block, chunk) of its first unit; chunk fastest, so a
     // span stays inside one row block as long as possible
     if (p.small) {
         const unsigned w = (unsigned)wid, W = (unsigned)p.warps, U = (unsigned)p.units;
         const unsigned u0 = w * U / W;
-        u = u0; uend = (w + 1) * U / W;
+        rem = (int)((w + 1) * U / W - u0);
         e = (int)(u0 / (unsigned)per_e);
         const unsigned r = u0 - (unsigned)e * (unsigned)per_e;
         rb = (int)(r / (unsigned)p.nch);
         ch = (int)(r - (unsigned)rb * (unsigned)p.nch);
     } else {
-        u = wid * p.units / p.warps; uend = (wid + 1) * p.units / p.warps;
+        const long long u = wid * p.units / p.warps;
+        rem = (int)((wid + 1) * p.units / p.warps - u);     // <= ceil(units / warps): the workspace budget keeps it far below 2^31
         e = (int)(u / per_e);
         const int r = (int)(u - (long long)e * per_e);
         rb = r / p.nch;
@@ -194,123 +214,155 @@ nn_fwd_kernel(const FwdParams p)
         for (long long i = tid; i < (long long)p.be * p.m * 3; i += nt) p.gxyz2[i] = 0.f;
         if (tid == 0 && p.zero_loss) *p.loss = 0.f;
     }
-    if (u >= uend) return;
+    if (rem <= 0) return;
 
-    float rx[kR], ry[kR], rz[kR], best[kR], snap[kR];
-    int tag[kR];
-    int held_e = -1, held_rb = -1, buf = 0;
-    long long held_u0 = 0;        // first unit this warp swept in the row block it holds
-    u64 *ckrow = nullptr;         // column keys of the row block it holds
-    prefetch_unit(p, e, rb, ch, srow, scol_all[warp][buf], true);
+    // rows and their running minima live in registers; the per-chunk bookkeeping (snapshot of the minima at the
+    // last chunk boundary, tags) lives in shared memory so the inner loop has the whole register file
+    float rx[kR], ry[kR], rz[kR], best[kR];
+    unsigned buf = 0;             // byte offset of the column buffer in use: 0 or kColBuf
+    prefetch_rows(p.xyz1 + (size_t)e * p.n * 3, p.n, rb, sm_s + kRowOff, lane);
+    prefetch_cols(p.xyz2 + (size_t)e * p.m * 3, p.m, ch, sm_s, lane);
+    cp_async_commit();
 
-    // store this warp's partial row keys of the row block it is leaving
-    auto flush_rows = [&]() {
-        const long long first = ((long long)held_e * p.nrb + held_rb) * p.nch;      // first unit of the row block
-        auto owner = [&](long long t) {
-            return p.small ? (long long)owner_of<unsigned>((unsigned)t, (unsigned)p.warps, (unsigned)p.units)
-                           : owner_of<long long>(t, p.warps, p.units);
-        };
-        // rank of this warp among the warps whose spans touch the row block: consecutive warps when every
-        // warp has work (units >= warps), one warp per unit otherwise -- the smaller of the two counts
-        const long long own = owner(first);
-        const int slot = (int)min(wid - own, held_u0 - first);
-        u64 *rk0 = p.rowkeys + (((size_t)held_e * p.nrb + held_rb) * p.nslot) * kRowsPerBlock + lane * kR;
-        u64 *rk = rk0 + (size_t)slot * kRowsPerBlock;
-#pragma unroll
-        for (int r = 0; r < kR; r++) rk[r] = ((u64)__float_as_uint(best[r]) << 32) | (unsigned)tag[r];
-        if (held_u0 == first) {
-            // the warp that swept the block's first unit also pads the slots no span reaches
-            const int used = (int)min(owner(first + p.nch - 1) - own + 1, (long long)p.nch);
-            for (int sl = used; sl < p.nsl; sl++) {
-#pragma unroll
-                for (int r = 0; r < kR; r++) rk0[(size_t)sl * kRowsPerBlock + r] = ~0ull;
-            }
-        }
-    };
+    for (;;) {
+        // ---- one row block: the chunks [ch0, ch_end) of (e, rb) belong to this warp
+        const int ch0 = ch;
+        const int ch_end = ch + min(p.nch - ch, rem);
+        rem -= ch_end - ch;        // > 0: the span goes on into the next row block (then ch_end == nch)
+        const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
+        int kcol = ch * kChunk + lane;
+        u64 *ck = p.colkeys + ((size_t)e * p.nrb + rb) * p.m + kcol;
 
-    for (; u < uend; u++) {
         cp_async_wait_all();
         __syncwarp();
-        if (e != held_e || rb != held_rb) {
-            if (held_e >= 0) flush_rows();
-            const float4 *src = reinterpret_cast<const float4 *>(srow + lane * kR * 3);
+        {
             float tmp[kR * 3];
 #pragma unroll
             for (int i = 0; i < kR * 3 / 4; i++) {
-                const float4 v = src[i];
+                const float4 v = lds128(sm_s + kRowOff + lane * (kR * 12) + i * 16);
                 tmp[4 * i] = v.x; tmp[4 * i + 1] = v.y; tmp[4 * i + 2] = v.z; tmp[4 * i + 3] = v.w;
             }
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 rx[r] = tmp[3 * r]; ry[r] = tmp[3 * r + 1]; rz[r] = tmp[3 * r + 2];
-                best[r] = snap[r] = __int_as_float(0x7f800000);
-                tag[r] = 0;
+                best[r] = __int_as_float(0x7f800000);
             }
-            held_e = e; held_rb = rb; held_u0 = u;
-            ckrow = p.colkeys + ((size_t)e * p.nrb + rb) * p.m;
+#pragma unroll
+            for (int h = 0; h < kR / 4; h++) {
+                sts128(sm_s + kSnapOff + h * 512 + lane * 16, 0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u);
+                sts128(sm_s + kTagOff + h * 512 + lane * 16, 0u, 0u, 0u, 0u);
+            }
         }
         __syncwarp();      // every lane has its rows in registers: the row buffer may be refilled
-        // successor unit without divisions: chunk fastest, then row block, then element
-        int e2 = e, rb2 = rb, ch2 = ch + 1;
-        if (ch2 == p.nch) { ch2 = 0; if (++rb2 == p.nrb) { rb2 = 0; e2++; } }
-        if (u + 1 < uend) prefetch_unit(p, e2, rb2, ch2, srow, scol_all[warp][buf ^ 1], ch2 == 0);
 
-        // ---- 256 rows x 32 columns
-        u64 *skey = skey_all[warp];
-        unsigned ca = smem_u32(scol_all[warp][buf]), ka = smem_u32(skey);
-        const unsigned cend = ca + kChunk * (unsigned)sizeof(float4);
-        const int lane0 = lane == 0;
-        float4 qn = lds128(ca);
-#pragma unroll kUnroll
-        do {
-            // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
-            // independent chains, issued back to back so their fixed latencies overlap
-            unsigned bits[kGroup];
-#pragma unroll
-            for (int g = 0; g < kGroup; g += 2) {
-                // two columns at a time so the minima can use the three-input FMNMX3 (two mins per issue slot;
-                // measured on B200 at 1.15 cycles per min against 1.65 for the two-input form)
-                const float4 q0 = qn;
-                const float4 q1 = lds128(ca + (g + 1) * (unsigned)sizeof(float4));
-                qn = lds128(ca + (g + 2) * (unsigned)sizeof(float4));   // next pair's first record is in flight during this pair's math
-                float d0[kR], d1[kR];
-#pragma unroll
-                for (int r = 0; r < kR; r++) {
-                    d0[r] = pnae_sqdist(q0.x - rx[r], q0.y - ry[r], q0.z - rz[r]);
-                    d1[r] = pnae_sqdist(q1.x - rx[r], q1.y - ry[r], q1.z - rz[r]);
-                    best[r] = min3f(best[r], d0[r], d1[r]);
-                }
-                // column minima over this lane's rows; d >= 0: unsigned order == float order
-                static_assert(kR == 8, "column tree below is written for 8 rows per lane");
-                bits[g] = __float_as_uint(fminf(min3f(min3f(min3f(d0[0], d0[1], d0[2]), d0[3], d0[4]), d0[5], d0[6]), d0[7]));
-                bits[g + 1] = __float_as_uint(fminf(min3f(min3f(min3f(d1[0], d1[1], d1[2]), d1[3], d1[4]), d1[5], d1[6]), d1[7]));
+        for (;;) {
+            // successor unit's data arrives while this chunk is swept
+            if (ch + 1 < ch_end) {
+                prefetch_cols(p2, p.m, ch + 1, sm_s + (buf ^ kColBuf), lane);
+            } else if (rem > 0) {
+                int e2 = e, rb2 = rb + 1;
+                if (rb2 == p.nrb) { rb2 = 0; e2++; }
+                prefetch_rows(p.xyz1 + (size_t)e2 * p.n * 3, p.n, rb2, sm_s + kRowOff, lane);
+                prefetch_cols(p.xyz2 + (size_t)e2 * p.m * 3, p.m, 0, sm_s + (buf ^ kColBuf), lane);
             }
-            unsigned mn[kGroup], who[kGroup];
+            cp_async_commit();
+
+            // ---- 256 rows x 32 columns
+            unsigned ca = sm_s + buf;                      // column records; this group's keys go to ca-relative ka
+            unsigned ka = sm_s + kKeyOff;
+            const unsigned cend = ca + kChunk * (unsigned)sizeof(float4);
+            float4 qn = lds128(ca);
+#pragma unroll kUnroll
+            do {
+                // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
+                // independent chains, issued back to back so their fixed latencies overlap
+                unsigned bits[kGroup];
 #pragma unroll
-            for (int g = 0; g < kGroup; g++) mn[g] = __reduce_min_sync(0xffffffffu, bits[g]);
+                for (int g = 0; g < kGroup; g += 2) {
+                    // two columns at a time so the minima can use the three-input FMNMX3
+                    const float4 q0 = qn;
+                    const float4 q1 = lds128(ca + (g + 1) * (unsigned)sizeof(float4));
+                    qn = lds128(ca + (g + 2) * (unsigned)sizeof(float4));   // next pair's first record is in flight during this pair's math
+                    float d0[kR], d1[kR];
 #pragma unroll
-            for (int g = 0; g < kGroup; g++) who[g] = __ballot_sync(0xffffffffu, bits[g] == mn[g]);
-            static_assert(kGroup == 4, "two 16-byte key stores per group");
-            sts128_if(lane0, ka, who[0], mn[0], who[1], mn[1]);          // u64 key = min bits << 32 | ballot
-            sts128_if(lane0, ka + 16, who[2], mn[2], who[3], mn[3]);
-            ca += kGroup * (unsigned)sizeof(float4);
-            ka += kGroup * (unsigned)sizeof(u64);
-        } while (ca != cend);
-        __syncwarp();
-        const u64 mykey = skey[lane];                    // lane c carries the key of column c of this chunk
-        __syncwarp();
-        // a strict decrease during this chunk => the row's running minimum first appears here
+                    for (int r = 0; r < kR; r++) {
+                        d0[r] = pnae_sqdist(q0.x - rx[r], q0.y - ry[r], q0.z - rz[r]);
+                        d1[r] = pnae_sqdist(q1.x - rx[r], q1.y - ry[r], q1.z - rz[r]);
+                        best[r] = min3f(best[r], d0[r], d1[r]);
+                    }
+                    // column minima over this lane's rows; d >= 0: unsigned order == float order
+                    static_assert(kR == 8, "column tree below is written for 8 rows per lane");
+                    bits[g] = __float_as_uint(fminf(min3f(min3f(min3f(d0[0], d0[1], d0[2]), d0[3], d0[4]), d0[5], d0[6]), d0[7]));
+                    bits[g + 1] = __float_as_uint(fminf(min3f(min3f(min3f(d1[0], d1[1], d1[2]), d1[3], d1[4]), d1[5], d1[6]), d1[7]));
+                }
+                unsigned mn[kGroup], who[kGroup];
 #pragma unroll
-        for (int r = 0; r < kR; r++) {
-            if (best[r] < snap[r]) tag[r] = ch;
-            snap[r] = best[r];
+                for (int g = 0; g < kGroup; g++) mn[g] = __reduce_min_sync(0xffffffffu, bits[g]);
+#pragma unroll
+                for (int g = 0; g < kGroup; g++) who[g] = __ballot_sync(0xffffffffu, bits[g] == mn[g]);
+                static_assert(kGroup == 4, "two 16-byte key stores per group");
+                sts128_if(lane == 0, ka, who[0], mn[0], who[1], mn[1]);          // u64 key = min bits << 32 | ballot
+                sts128_if(lane == 0, ka + 16, who[2], mn[2], who[3], mn[3]);
+                ca += kGroup * (unsigned)sizeof(float4);
+                ka += kGroup * (unsigned)sizeof(u64);
+            } while (ca != cend);
+            __syncwarp();
+            const u64 mykey = lds64(sm_s + kKeyOff + lane * 8);     // lane c carries the key of column c of this chunk
+            __syncwarp();
+            // a strict decrease during this chunk => the row's running minimum first appears here
+#pragma unroll
+            for (int h = 0; h < kR / 4; h++) {
+                const float4 sn = lds128(sm_s + kSnapOff + h * 512 + lane * 16);
+                const float4 tg = lds128(sm_s + kTagOff + h * 512 + lane * 16);
+                const unsigned uch = (unsigned)ch;
+                sts128(sm_s + kTagOff + h * 512 + lane * 16,
+                       best[4 * h] < sn.x ? uch : __float_as_uint(tg.x), best[4 * h + 1] < sn.y ? uch : __float_as_uint(tg.y),
+                       best[4 * h + 2] < sn.z ? uch : __float_as_uint(tg.z), best[4 * h + 3] < sn.w ? uch : __float_as_uint(tg.w));
+                sts128(sm_s + kSnapOff + h * 512 + lane * 16, __float_as_uint(best[4 * h]), __float_as_uint(best[4 * h + 1]),
+                       __float_as_uint(best[4 * h + 2]), __float_as_uint(best[4 * h + 3]));
+            }
+            if (kcol < p.m) *ck = mykey;
+            ck += kChunk; kcol += kChunk;
+            buf ^= kColBuf;
+            if (++ch == ch_end) break;
+            cp_async_wait_all();
+            __syncwarp();
         }
-        const int k = ch * kChunk + lane;
-        if (k < p.m) ckrow[k] = mykey;
-        buf ^= 1;
-        e = e2; rb = rb2; ch = ch2;
+
+        // ---- leaving the row block: store this warp's partial row keys
+        {
+            const long long first = ((long long)e * p.nrb + rb) * p.nch;      // first unit of the row block
+            auto owner = [&](long long t) {
+                return p.small ? (long long)owner_of<unsigned>((unsigned)t, (unsigned)p.warps, (unsigned)p.units)
+                               : owner_of<long long>(t, p.warps, p.units);
+            };
+            // rank of this warp among the warps whose spans touch the row block: consecutive warps when every
+            // warp has work (units >= warps), one warp per unit otherwise -- the smaller of the two counts
+            const long long own = owner(first);
+            const int slot = (int)min((long long)wid - own, (long long)ch0);
+            u64 *rk0 = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + lane * kR;
+            u64 *rk = rk0 + (size_t)slot * kRowsPerBlock;
+#pragma unroll
+            for (int h = 0; h < kR / 4; h++) {
+                const float4 tg = lds128(sm_s + kTagOff + h * 512 + lane * 16);
+                rk[4 * h] = ((u64)__float_as_uint(best[4 * h]) << 32) | __float_as_uint(tg.x);
+                rk[4 * h + 1] = ((u64)__float_as_uint(best[4 * h + 1]) << 32) | __float_as_uint(tg.y);
+                rk[4 * h + 2] = ((u64)__float_as_uint(best[4 * h + 2]) << 32) | __float_as_uint(tg.z);
+                rk[4 * h + 3] = ((u64)__float_as_uint(best[4 * h + 3]) << 32) | __float_as_uint(tg.w);
+            }
+            if (ch0 == 0) {
+                // the warp that swept the block's first unit also pads the slots no span reaches
+                const int used = (int)min(owner(first + p.nch - 1) - own + 1, (long long)p.nch);
+                for (int sl = used; sl < p.nsl; sl++) {
+#pragma unroll
+                    for (int r = 0; r < kR; r++) rk0[(size_t)sl * kRowsPerBlock + r] = ~0ull;
+                }
+            }
+        }
+        if (rem <= 0) break;
+        ch = 0;
+        if (++rb == p.nrb) { rb = 0; e++; }
     }
-    flush_rows();
 }
 
 // Finalize launch: kFinLanes lanes per output point.  Each group reduces the point's partial

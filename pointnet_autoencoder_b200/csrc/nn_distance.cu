@@ -595,32 +595,57 @@ nn_bwd_kernel(int b, int n, const float *__restrict__ xyz1, int m, const float *
     asm volatile("griddepcontrol.launch_dependents;");        // a following sweep may set itself up while this grid runs
     asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: idx comes from the kernel before
     const int stride = cs * kBwdThreads;
+    constexpr int kKeep = 4;      // points per thread whose scatter term stays in registers across the barrier
+    const bool keep = (long long)n + m <= (long long)stride * kKeep;
     for (int e = blockIdx.x / cs; e < b; e += nclusters) {
         const float *p1 = xyz1 + (size_t)e * n * 3, *p2 = xyz2 + (size_t)e * m * 3;
         float *g1 = grad_xyz1 + (size_t)e * n * 3, *g2 = grad_xyz2 + (size_t)e * m * 3;
-        for (int phase = 0; phase < 2; phase++) {
-            for (int t = tid; t < n + m; t += stride) {
-                const bool second = t >= n;
-                const int j = second ? t - n : t;
-                const float *a = (second ? p2 : p1) + j * 3;
-                const int j2 = second ? idx2[(size_t)e * m + j] : idx1[(size_t)e * n + j];
-                const float *c = (second ? p1 : p2) + j2 * 3;
-                const float g = __fmul_rn(second ? grad_dist2[(size_t)e * m + j] : grad_dist1[(size_t)e * n + j], 2.0f);
-                const float vx = __fmul_rn(g, __fsub_rn(__ldg(a), __ldg(c)));
-                const float vy = __fmul_rn(g, __fsub_rn(__ldg(a + 1), __ldg(c + 1)));
-                const float vz = __fmul_rn(g, __fsub_rn(__ldg(a + 2), __ldg(c + 2)));
-                if (phase == 0) {
-                    float *ga = (second ? g2 : g1) + j * 3;
-                    ga[0] = vx; ga[1] = vy; ga[2] = vz;
-                } else {
-                    float *gc = (second ? g1 : g2) + j2 * 3;
-                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+        // v = 2 g (a_j - c_idx[j]) of point t (t < n: a point of xyz1, else of xyz2) and where its scatter half goes
+        auto term = [&](int t, float &vx, float &vy, float &vz, float *&ga, float *&gc) {
+            const bool second = t >= n;
+            const int j = second ? t - n : t;
+            const float *a = (second ? p2 : p1) + j * 3;
+            const int j2 = second ? idx2[(size_t)e * m + j] : idx1[(size_t)e * n + j];
+            const float *c = (second ? p1 : p2) + j2 * 3;
+            const float g = __fmul_rn(second ? grad_dist2[(size_t)e * m + j] : grad_dist1[(size_t)e * n + j], 2.0f);
+            vx = __fmul_rn(g, __fsub_rn(__ldg(a), __ldg(c)));
+            vy = __fmul_rn(g, __fsub_rn(__ldg(a + 1), __ldg(c + 1)));
+            vz = __fmul_rn(g, __fsub_rn(__ldg(a + 2), __ldg(c + 2)));
+            ga = (second ? g2 : g1) + j * 3;
+            gc = (second ? g1 : g2) + j2 * 3;
+        };
+        if (keep) {
+            // the usual case (n + m <= 4 * cluster threads): every term is evaluated once
+            float kx[kKeep], ky[kKeep], kz[kKeep];
+            float *kc[kKeep];
+#pragma unroll
+            for (int i = 0; i < kKeep; i++) {
+                const int t = tid + i * stride;
+                kc[i] = nullptr;
+                if (t < n + m) {
+                    float *ga;
+                    term(t, kx[i], ky[i], kz[i], ga, kc[i]);
+                    ga[0] = kx[i]; ga[1] = ky[i]; ga[2] = kz[i];
                 }
             }
             // the barrier orders phase 1's plain stores before phase 2's atomics on the same addresses
             // (release/acquire at cluster scope; all of an element's traffic stays inside its cluster)
-            if (phase == 0) cluster.sync();
+            cluster.sync();
+#pragma unroll
+            for (int i = 0; i < kKeep; i++)
+                if (kc[i] != nullptr) { atomicAdd(kc[i], -kx[i]); atomicAdd(kc[i] + 1, -ky[i]); atomicAdd(kc[i] + 2, -kz[i]); }
+        } else {
+            for (int phase = 0; phase < 2; phase++) {
+                for (int t = tid; t < n + m; t += stride) {
+                    float vx, vy, vz, *ga, *gc;
+                    term(t, vx, vy, vz, ga, gc);
+                    if (phase == 0) { ga[0] = vx; ga[1] = vy; ga[2] = vz; }
+                    else { atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz); }
+                }
+                if (phase == 0) cluster.sync();
+            }
         }
+        // the next round works on another element's buffers: no barrier needed between rounds
     }
 }
 

@@ -381,14 +381,41 @@ constexpr int kFinLanes = PNAE_NN_FINLANES;
 #define PNAE_NN_FINOCC 8
 #endif
 constexpr int kFinThreads = PNAE_NN_FINTHREADS;
+#ifndef PNAE_NN_FINWAVES
+#define PNAE_NN_FINWAVES 1            // finalize grid size in units of "one resident wave"
+#endif
 constexpr int kFinOcc = PNAE_NN_FINOCC;       // resident CTAs per SM the finalize is compiled for
 
 // FUSED: additionally accumulate loss = w1*sum(dist1) + w2*sum(dist2) and its gradient
 //   d/d a_j = 2 w (a_j - c_nn(j)),   d/d c_nn(j) = -2 w (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148 with
 // grad_dist == w), so the Chamfer loss of models/model.py:80-83 needs no separate gradient launch and no dist/idx
 // round trip.  dist/idx outputs are optional on this path.
-// Grid: x = blocks of kFinThreads/kFinLanes points of one element (its n points of xyz1, then its m of xyz2),
-// y = element: no divisions anywhere.
+// Grid: y = element, x = CTAs sharing that element's n + m points (its points of xyz1, then those of xyz2) in
+// blocks of kFinThreads/kFinLanes: no divisions anywhere.  The grid is sized to be resident at once; each lane
+// group walks its points with the NEXT point's coordinates and partial keys already in flight while the current
+// point's candidates are fetched and compared, so a point costs one exposed L2 round trip instead of two.
+struct FinPoint {
+    float x, y, z;
+    u64 v[4];          // first four partial keys of this lane (slot / row block  sub + t * kFinLanes)
+};
+
+__device__ __forceinline__ void fin_issue(const FwdParams &p, int e, int pt, int sub, FinPoint &a)
+{
+    const int per_e = p.n + p.m;
+    const int r = min(pt, per_e - 1);
+    const bool row = r < p.n;
+    const int j = row ? r : r - p.n;
+    const float *src = (row ? p.xyz1 + (size_t)e * p.n * 3 : p.xyz2 + (size_t)e * p.m * 3) + (size_t)j * 3;
+    a.x = __ldg(src); a.y = __ldg(src + 1); a.z = __ldg(src + 2);
+    const int rb = j / kRowsPerBlock;
+    const u64 *base = row ? p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot + sub) * kRowsPerBlock + (j - rb * kRowsPerBlock)
+                          : p.colkeys + ((size_t)e * p.nrb + sub) * p.m + j;
+    const size_t stride = (size_t)kFinLanes * (row ? kRowsPerBlock : p.m);
+    const int count = row ? p.nsl : p.nrb;
+#pragma unroll
+    for (int t = 0; t < 4; t++) a.v[t] = (sub + t * kFinLanes < count) ? __ldcg(base + t * stride) : ~0ull;
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(kFinThreads, kFinOcc)
 nn_finalize_kernel(const FwdParams p)
@@ -398,11 +425,9 @@ nn_finalize_kernel(const FwdParams p)
     // shuffles stay inside one point's lane group: a warp whose points straddle the xyz1/xyz2 boundary of an
     // element (n not a multiple of 32/kFinLanes) takes both branches below, so a full-warp mask would be divergent
     const unsigned gmask = (unsigned)((1ull << kFinLanes) - 1ull) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
+    constexpr int kPtsPerCta = kFinThreads / kFinLanes;
     const int per_e = p.n + p.m;
     const int e = blockIdx.y;
-    const int pt = (int)(blockIdx.x * (unsigned)(kFinThreads / kFinLanes) + threadIdx.x / kFinLanes);
-    const bool live = pt < per_e;
-    const int r = live ? pt : per_e - 1;
     const float *p1 = p.xyz1 + (size_t)e * p.n * 3;
     const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
     // wide candidate loads need the element bases 16-byte (xyz2) / 8-byte (xyz1) aligned
@@ -410,124 +435,134 @@ nn_finalize_kernel(const FwdParams p)
     const bool vec1 = (reinterpret_cast<size_t>(p.xyz1) & 7) == 0 && (p.n & 1) == 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // launched with programmatic stream serialization
     asm volatile("griddepcontrol.launch_dependents;");        // the gradient kernel may queue up behind us the same way
-    if (r < p.n) {
-        // point j of xyz1 -> dist1 / idx1
-        const int j = r;
-        const float x = __ldg(p1 + j * 3), y = __ldg(p1 + j * 3 + 1), z = __ldg(p1 + j * 3 + 2);
-        const int rb = j / kRowsPerBlock;
-        const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
-        u64 key = ~0ull;       // (min bits, chunk): u64 order = lower distance, then lower chunk
-        for (int sl = sub; sl < p.nsl; sl += 4 * kFinLanes) {
-            u64 v[4];
+    int pt = (int)(blockIdx.x * (unsigned)kPtsPerCta + threadIdx.x / kFinLanes);
+    const int step = (int)(gridDim.x * (unsigned)kPtsPerCta);
+    const int pt_end = (per_e + kPtsPerCta - 1) / kPtsPerCta * kPtsPerCta;      // warp-uniform trip count
+    FinPoint nxt;
+    if (pt < pt_end) fin_issue(p, e, pt, sub, nxt);
+    for (; pt < pt_end; pt += step) {
+        const FinPoint cur = nxt;
+        const bool live = pt < per_e;
+        const int r = live ? pt : per_e - 1;
+        const float x = cur.x, y = cur.y, z = cur.z;
+        if (r < p.n) {
+            // point j of xyz1 -> dist1 / idx1
+            const int j = r;
+            u64 key = min(min(cur.v[0], cur.v[1]), min(cur.v[2], cur.v[3]));   // (min bits, chunk): lower distance, then lower chunk
+            if (p.nsl > 4 * kFinLanes) {
+                const int rb = j / kRowsPerBlock;
+                const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
+                for (int sl = sub + 4 * kFinLanes; sl < p.nsl; sl += kFinLanes) key = min(key, __ldcg(rk + (size_t)sl * kRowsPerBlock));
+            }
 #pragma unroll
-            for (int t = 0; t < 4; t++) v[t] = (sl + t * kFinLanes < p.nsl) ? __ldcg(rk + (size_t)(sl + t * kFinLanes) * kRowsPerBlock) : ~0ull;
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
+            const float want = __uint_as_float((unsigned)(key >> 32));
+            const int k0 = (int)(unsigned)key * kChunk;
+            constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
+            float cf[kPer * 3];
+            if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
+                const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
 #pragma unroll
-            for (int t = 0; t < 4; t++) key = min(key, v[t]);
-        }
+                for (int c = 0; c < kPer * 3 / 4; c++) {
+                    const float4 v = __ldg(src + c);
+                    cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
+                }
+            } else {
 #pragma unroll
-        for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
-        const float want = __uint_as_float((unsigned)(key >> 32));
-        const int k0 = (int)(unsigned)key * kChunk;
-        constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
-        float cf[kPer * 3];
-        if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
-            const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
+                for (int c = 0; c < kPer; c++) {
+                    const int k = min(k0 + sub * kPer + c, p.m - 1);
+                    cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
+                }
+            }
+            if (pt + step < pt_end) fin_issue(p, e, pt + step, sub, nxt);   // in flight while the candidates arrive
+            int found = 0x7fffffff;
 #pragma unroll
-            for (int c = 0; c < kPer * 3 / 4; c++) {
-                const float4 v = __ldg(src + c);
-                cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+            if (live && sub == 0) {
+                const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
+                if (p.dist1 != nullptr) {
+                    p.dist1[(size_t)e * p.n + j] = want;
+                    p.idx1[(size_t)e * p.n + j] = nn;
+                }
+                if (FUSED) {
+                    loss_acc = fmaf(p.w1, want, loss_acc);
+                    const float g = __fmul_rn(p.w1, 2.0f);
+                    float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
         } else {
-#pragma unroll
-            for (int c = 0; c < kPer; c++) {
-                const int k = min(k0 + sub * kPer + c, p.m - 1);
-                cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
-            }
-        }
-        int found = 0x7fffffff;
-#pragma unroll
-        for (int c = kPer - 1; c >= 0; c--)
-            if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
-#pragma unroll
-        for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
-        if (live && sub == 0) {
-            const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
-            if (p.dist1 != nullptr) {
-                p.dist1[(size_t)e * p.n + j] = want;
-                p.idx1[(size_t)e * p.n + j] = nn;
-            }
-            if (FUSED) {
-                loss_acc = __fmul_rn(p.w1, want);
-                const float g = __fmul_rn(p.w1, 2.0f);
-                float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
-                const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
-                const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
-                atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
-                atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
-            }
-        }
-    } else {
-        // point k of xyz2 -> dist2 / idx2
-        const int k = r - p.n;
-        const float x = __ldg(p2 + k * 3), y = __ldg(p2 + k * 3 + 1), z = __ldg(p2 + k * 3 + 2);
-        const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
-        u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
-        unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
-        for (int rb = sub; rb < p.nrb; rb += 4 * kFinLanes) {
-            u64 v[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) v[t] = (rb + t * kFinLanes < p.nrb) ? __ldcg(ck + (size_t)(rb + t * kFinLanes) * p.m) : ~0ull;
+            // point k of xyz2 -> dist2 / idx2
+            const int k = r - p.n;
+            u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
+            unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                const u64 cand = (v[t] & 0xffffffff00000000ull) | (unsigned)(rb + t * kFinLanes);
-                if (rb + t * kFinLanes < p.nrb && cand < key) { key = cand; who = (unsigned)v[t]; }
+                const int rb = sub + t * kFinLanes;
+                const u64 cand = (cur.v[t] & 0xffffffff00000000ull) | (unsigned)rb;
+                if (rb < p.nrb && cand < key) { key = cand; who = (unsigned)cur.v[t]; }
             }
-        }
-#pragma unroll
-        for (int o = kFinLanes / 2; o > 0; o >>= 1) {
-            const u64 k2 = __shfl_xor_sync(gmask, key, o);
-            const unsigned w2 = __shfl_xor_sync(gmask, who, o);
-            if (k2 < key) { key = k2; who = w2; }
-        }
-        const int rbw = (int)(unsigned)key;
-        const float want = __uint_as_float((unsigned)(key >> 32));
-        const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
-        constexpr int kPer = kR / kFinLanes;
-        float cf[kPer * 3];
-        if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
-            const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
-#pragma unroll
-            for (int c = 0; c < kPer * 3 / 2; c++) {
-                const float2 v = __ldg(src + c);
-                cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
+            if (p.nrb > 4 * kFinLanes) {
+                const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
+                for (int rb = sub + 4 * kFinLanes; rb < p.nrb; rb += kFinLanes) {
+                    const u64 v = __ldcg(ck + (size_t)rb * p.m);
+                    const u64 cand = (v & 0xffffffff00000000ull) | (unsigned)rb;
+                    if (cand < key) { key = cand; who = (unsigned)v; }
+                }
             }
-        } else {
 #pragma unroll
-            for (int c = 0; c < kPer; c++) {
-                const int j = min(j0 + sub * kPer + c, p.n - 1);
-                cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) {
+                const u64 k2 = __shfl_xor_sync(gmask, key, o);
+                const unsigned w2 = __shfl_xor_sync(gmask, who, o);
+                if (k2 < key) { key = k2; who = w2; }
             }
-        }
-        int found = 0x7fffffff;
+            const int rbw = (int)(unsigned)key;
+            const float want = __uint_as_float((unsigned)(key >> 32));
+            const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
+            constexpr int kPer = kR / kFinLanes;
+            float cf[kPer * 3];
+            if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
+                const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
 #pragma unroll
-        for (int c = kPer - 1; c >= 0; c--)
-            if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
+                for (int c = 0; c < kPer * 3 / 2; c++) {
+                    const float2 v = __ldg(src + c);
+                    cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
+                }
+            } else {
 #pragma unroll
-        for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
-        if (live && sub == 0) {
-            const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
-            if (p.dist2 != nullptr) {
-                p.dist2[(size_t)e * p.m + k] = want;
-                p.idx2[(size_t)e * p.m + k] = nn;
+                for (int c = 0; c < kPer; c++) {
+                    const int j = min(j0 + sub * kPer + c, p.n - 1);
+                    cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
+                }
             }
-            if (FUSED) {
-                loss_acc = __fmul_rn(p.w2, want);
-                const float g = __fmul_rn(p.w2, 2.0f);
-                float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
-                const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
-                const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
-                atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
-                atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+            if (pt + step < pt_end) fin_issue(p, e, pt + step, sub, nxt);   // in flight while the candidates arrive
+            int found = 0x7fffffff;
+#pragma unroll
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+            if (live && sub == 0) {
+                const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
+                if (p.dist2 != nullptr) {
+                    p.dist2[(size_t)e * p.m + k] = want;
+                    p.idx2[(size_t)e * p.m + k] = nn;
+                }
+                if (FUSED) {
+                    loss_acc = fmaf(p.w2, want, loss_acc);
+                    const float g = __fmul_rn(p.w2, 2.0f);
+                    float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
         }
     }
@@ -707,7 +742,10 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_fwd_kernel, p));
-        cfg.gridDim = dim3((unsigned)((n + m + kFinThreads / kFinLanes - 1) / (kFinThreads / kFinLanes)), (unsigned)p.be);
+        // resident at once: sms * kFinOcc CTAs shared out over the elements (at least one, at most all its blocks)
+        const int fin_blocks = (n + m + kFinThreads / kFinLanes - 1) / (kFinThreads / kFinLanes);
+        const int fin_x = max(1, min(fin_blocks, (sms * kFinOcc * PNAE_NN_FINWAVES + p.be - 1) / p.be));
+        cfg.gridDim = dim3((unsigned)fin_x, (unsigned)p.be);
         cfg.blockDim = dim3(kFinThreads);
         if (loss != nullptr) PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<true>, p));
         else PNAE_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_finalize_kernel<false>, p));

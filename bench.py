@@ -331,7 +331,7 @@ def run_product(args):
                    "launch": "CUDA graphs of %d consecutive steps (3 kernels per step: sweep, finalize, gradient), one replay per %d steps" % (SPG, SPG),
                    "upstream_grad": "100/(B*N) (models/model.py:81-83)"},
         "roofline": {"bound": "fp32", "kernel": "nn_distance forward (nn_fwd_kernel sweep + nn_finalize_kernel)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": 1606400,
+                     "frac": achieved / fp32_peak, "traffic": 1624064,
                      "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/r1_microbench_b200.txt)" % (sms.value, sm_max),
                      "traffic_source": "dram__bytes_read+write of nn_fwd_kernel, ncu --set full (profiles/r1_ncu_full_summary.txt); algorithmic bytes %d" % alg_bytes,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,

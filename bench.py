@@ -203,7 +203,7 @@ def run_reference(args):
                              "sample": "full batch, every step, %s" % _cpu_model()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -348,7 +348,7 @@ def run_product(args):
         line["cpu_baseline"] = cpu_baseline(threads=1, reps=3)
     if world == 1 and not args.no_emd:
         line["extra"] = emd_numbers(dev)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,7 +377,25 @@ def emd_numbers(dev):
             "emd_frac_of_fp32_peak": 423 * pairs / ((am + mc) * 1e-3) / peak, "data": "S-chair"}
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """the ONE JSON line, on the real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print on fd 1 meanwhile (NCCL's version banner at
+    # N>1, for one) is sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)

@@ -67,6 +67,9 @@ struct FwdParams {
     float w1, w2;
     int zero_loss;     // this launch is the first chunk of the call: it also zeroes *loss
     int small;         // (units + 1) * warps and the point count fit 32 bits: cheap unsigned index arithmetic
+#ifdef PNAE_NN_TRACE
+    unsigned long long *trace;   // tools/trace_nn.py: [warp][4] globaltimer stamps (entry, after wait, first data, exit)
+#endif
 };
 
 // three-input minimum (FMNMX3); NaN operands are ignored like fminf
@@ -180,6 +183,17 @@ nn_fwd_kernel(const FwdParams p)
     // let the finalize launch become resident as SMs drain (it blocks in cudaGridDependencySynchronize
     // until every CTA of this grid has finished and flushed): its launch latency hides under the sweep's tail
     asm volatile("griddepcontrol.launch_dependents;");
+#ifdef PNAE_NN_TRACE
+    auto stamp = [&](int i) {
+        if (p.trace != nullptr && lane == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[((size_t)blockIdx.x * kWarps + warp) * 4 + i] = t;
+        }
+    };
+    stamp(0);
+    bool traced = false;
+#endif
     const unsigned sm_s = smem_u32(&smem_all[warp]);       // the one shared-memory base register of this warp
     const int wid = blockIdx.x * kWarps + warp;
     const int per_e = p.nrb * p.nch;
@@ -206,6 +220,9 @@ nn_fwd_kernel(const FwdParams p)
     // this grid is itself launched with programmatic stream serialization: everything above (parameters only)
     // may run while the kernel before it drains; global memory may only be touched from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef PNAE_NN_TRACE
+    stamp(1);
+#endif
     if (p.gxyz1 != nullptr) {
         // fused loss+gradient: the finalize accumulates into these with atomics, so clear them here (it cannot
         // start touching them before this whole grid has finished)
@@ -235,6 +252,9 @@ nn_fwd_kernel(const FwdParams p)
 
         cp_async_wait_all();
         __syncwarp();
+#ifdef PNAE_NN_TRACE
+        if (!traced) { stamp(2); traced = true; }
+#endif
         {
             float tmp[kR * 3];
 #pragma unroll
@@ -363,6 +383,9 @@ nn_fwd_kernel(const FwdParams p)
         ch = 0;
         if (++rb == p.nrb) { rb = 0; e++; }
     }
+#ifdef PNAE_NN_TRACE
+    stamp(3);
+#endif
 }
 
 // Finalize launch: kFinLanes lanes per output point.  Each group reduces the point's partial
@@ -729,6 +752,9 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         const long long groups = (long long)p.be * ((long long)n + m);
         const bool small = !force64 && groups < (1ll << 31) && (p.units + 1) * p.warps < (1ll << 32);
         p.small = small;
+#ifdef PNAE_NN_TRACE
+        { const char *tp = getenv("PNAE_NN_TRACE_PTR"); p.trace = tp ? (unsigned long long *)strtoull(tp, nullptr, 16) : nullptr; }
+#endif
         // slots one row block can need in this launch: its nch units meet at most ceil(nch / shortest span) + 1 spans
         const long long span = p.units / p.warps;
         p.nsl = span >= 1 ? (int)min((long long)pl.nslot, (pl.nch + span - 1) / span + 1) : pl.nslot;

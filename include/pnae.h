@@ -58,6 +58,12 @@ PNAE_API int pnae_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* Scratch bytes pnae_nn_distance_fwd needs for these sizes (may be 0). */
 PNAE_API size_t pnae_nn_distance_workspace_bytes(int b, int n, int m);
 
+/* Introspection (host only, no device access): how pnae_nn_distance_fwd would split these sizes on a device
+ * with sm_count SMs.  plan[9] = { row blocks, column chunks, row-key slots per row block in the workspace,
+ * elements per launch, sweep warps, slots in use by a full launch, slots in use by the last launch,
+ * rows per block, columns per chunk }.  tests/test_cabi.py checks the stream-K slot arithmetic against it. */
+PNAE_API int pnae_nn_distance_plan(int b, int n, int m, int sm_count, int *plan);
+
 /* Replaces NmDistanceKernelLauncher (tf_ops/nn_distance/tf_nndistance_g.cu:128-131).
  * dist1[i,j] = min_k |xyz1[i,j]-xyz2[i,k]|^2 (squared), idx1 = lowest-index argmin;
  * dist2/idx2 the same with the roles swapped.  n, m >= 1. */
@@ -102,6 +108,11 @@ PNAE_API int pnae_graph_launch(void *handle, void *stream);
 PNAE_API int pnae_graph_destroy(void *handle);
 
 /* ---- approximate earth mover's distance -------------------------------- */
+
+/* Introspection (host only, no device access): plan[6] = { cooperative grid size, partial-sum slots per own
+ * block, max(n,m), own points per task, streamed points per task, threads per CTA } for a device with sm_count
+ * SMs.  tests/test_cabi.py checks the sweep's slot arithmetic against it. */
+PNAE_API int pnae_approx_match_plan(int b, int n, int m, int sm_count, int *plan);
 
 /* Scratch bytes pnae_approx_match needs (the reference's `temp`, tf_approxmatch.cpp:168). */
 PNAE_API size_t pnae_approx_match_workspace_bytes(int b, int n, int m);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pnae_last_error": (C.c_char_p, []),
     "pnae_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "pnae_nn_distance_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pnae_nn_distance_plan": (_i, [_i, _i, _i, _i, _vp]),
     "pnae_nn_distance_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pnae_nn_distance_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnae_chamfer_loss_grad": (_i, [_i, _i, _vp, _i, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -38,6 +39,7 @@ SIGNATURES = {
     "pnae_graph_launch": (_i, [_vp, _vp]),
     "pnae_graph_destroy": (_i, [_vp]),
     "pnae_approx_match_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pnae_approx_match_plan": (_i, [_i, _i, _i, _i, _vp]),
     "pnae_approx_match": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pnae_match_from_factors": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pnae_match_cost_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -329,6 +329,14 @@ EmdPlan make_plan(int b, int n, int m, int sms)
 int pnae_match_from_factors_impl(int b, int n, int m, const float *xyz1, const float *xyz2,
                                  const float *factors, float *match, cudaStream_t st);
 
+extern "C" int pnae_approx_match_plan(int b, int n, int m, int sm_count, int *plan)
+{
+    PNAE_REQUIRE(b >= 1 && n >= 1 && m >= 1 && sm_count >= 1 && plan != nullptr, "approx_match_plan: invalid argument");
+    const EmdPlan pl = make_plan(b, n, m, sm_count);
+    plan[0] = pl.grid; plan[1] = pl.nslot; plan[2] = pl.maxnm; plan[3] = kOwn; plan[4] = kTs; plan[5] = kThreads;
+    return PNAE_OK;
+}
+
 extern "C" size_t pnae_approx_match_workspace_bytes(int b, int n, int m)
 {
     if (b <= 0 || n <= 0 || m <= 0) return 0;

@@ -629,6 +629,15 @@ FwdPlan make_plan(int b, int n, int m, int sms)
     return pl;
 }
 
+// slots one row block can need in a launch of `be` elements: its nch units meet at most
+// ceil(nch / shortest span) + 1 spans (every unit its own span when there are fewer units than warps)
+int launch_slots(const FwdPlan &pl, int be)
+{
+    const long long units = (long long)be * pl.nrb * pl.nch;
+    const long long span = units / pl.warps;
+    return span >= 1 ? (int)min((long long)pl.nslot, (pl.nch + span - 1) / span + 1) : pl.nslot;
+}
+
 // ---------------------------------------------------------------------------
 // Gradient: one cluster per batch element, one launch.
 //   phase 1 (plain stores)  grad_a[j]      = 2 g (a_j - c_idx[j])      for both clouds
@@ -715,6 +724,18 @@ extern "C" size_t pnae_nn_distance_workspace_bytes(int b, int n, int m)
     return make_plan(b, n, m, pnae_sm_count()).total;
 }
 
+extern "C" int pnae_nn_distance_plan(int b, int n, int m, int sm_count, int *plan)
+{
+    PNAE_REQUIRE(b >= 1 && n >= 1 && m >= 1 && sm_count >= 1 && plan != nullptr, "nn_distance_plan: invalid argument");
+    const FwdPlan pl = make_plan(b, n, m, sm_count);
+    plan[0] = pl.nrb; plan[1] = pl.nch; plan[2] = pl.nslot; plan[3] = pl.be;
+    plan[4] = (int)pl.warps;
+    plan[5] = launch_slots(pl, pl.be);                                     // full launches
+    plan[6] = launch_slots(pl, b % pl.be ? b % pl.be : pl.be);             // the last, possibly partial one
+    plan[7] = kRowsPerBlock; plan[8] = kChunk;
+    return PNAE_OK;
+}
+
 namespace {
 // shared launcher: plain forward (loss == NULL) or fused loss + gradient
 int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const float *xyz2,
@@ -755,9 +776,7 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
 #ifdef PNAE_NN_TRACE
         { const char *tp = getenv("PNAE_NN_TRACE_PTR"); p.trace = tp ? (unsigned long long *)strtoull(tp, nullptr, 16) : nullptr; }
 #endif
-        // slots one row block can need in this launch: its nch units meet at most ceil(nch / shortest span) + 1 spans
-        const long long span = p.units / p.warps;
-        p.nsl = span >= 1 ? (int)min((long long)pl.nslot, (pl.nch + span - 1) / span + 1) : pl.nslot;
+        p.nsl = launch_slots(pl, p.be);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency overlaps the previous kernel's tail
         attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -71,3 +71,74 @@ def test_product_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
                 assert "liboracle" not in src and "libref_" not in src, fn
+
+
+def _simulate_row_slots(be, nrb, nch, warps):
+    """The device's span / slot arithmetic of nn_fwd_kernel (csrc/nn_distance.cu), restated: every warp w owns
+    units [w*U//W, (w+1)*U//W) (chunk fastest); leaving a row block it stores its partial row keys in slot
+    min(w - owner(first unit of the block), its first chunk in the block).  Returns, per row block, the slots used."""
+    U = be * nrb * nch
+    owner = lambda t: ((t + 1) * warps - 1) // U
+    used = {}
+    for w in range(warps):
+        u, uend = w * U // warps, (w + 1) * U // warps
+        while u < uend:
+            blk, ch = divmod(u, nch)
+            seg = min(nch - ch, uend - u)
+            first = blk * nch
+            used.setdefault(blk, []).append(min(w - owner(first), ch))
+            u += seg
+    return used, owner
+
+
+@pytest.mark.parametrize("b,n,m,sms", [(32, 2048, 2048, 148), (1, 1, 1, 148), (3, 777, 333, 148), (2, 16384, 1024, 148),
+                                       (8, 4096, 4096, 148), (64, 64, 64, 148), (5, 300, 5000, 148), (1, 257, 33, 148),
+                                       (7, 2048, 2048, 4), (33, 40, 50, 1), (2, 1, 700, 148), (128, 2048, 2048, 148)])
+def test_chamfer_plan_slot_arithmetic(b, n, m, sms):
+    """Host logic of the Chamfer forward without a GPU: the launcher's slot bound covers every slot the sweep's
+    warps use, slots of one row block are distinct, and the slot-0 warp's pad range [used, nsl) is consistent."""
+    lib = _lib.load()
+    plan = (C.c_int * 9)()
+    assert lib.pnae_nn_distance_plan(b, n, m, sms, plan) == 0
+    nrb, nch, nslot, be, warps, nsl_full, nsl_last, rpb, cpc = list(plan)
+    assert nrb == -(-n // rpb) and nch == -(-m // cpc) and warps == sms * 16 and 1 <= be <= min(b, 65535)
+    for be_launch, nsl in {(be, nsl_full), (b % be or be, nsl_last)}:
+        assert 1 <= nsl <= nslot <= nch
+        used, owner = _simulate_row_slots(be_launch, nrb, nch, warps)
+        assert sorted(used) == list(range(be_launch * nrb))                  # every row block is flushed by someone
+        for blk, slots in used.items():
+            first = blk * nch
+            span_count = min(owner(first + nch - 1) - owner(first) + 1, nch)  # what the slot-0 warp computes as `used`
+            assert sorted(slots) == list(range(len(slots))), (blk, slots)     # distinct, dense from 0
+            assert len(slots) == span_count <= nsl, (blk, slots, span_count, nsl)
+
+
+@pytest.mark.parametrize("b,n,m,sms", [(32, 2048, 2048, 148), (1, 1, 1, 148), (3, 777, 333, 148), (2, 4096, 1024, 148),
+                                       (4, 2048, 2048, 148), (64, 64, 64, 148), (5, 300, 5000, 148), (1, 513, 129, 148),
+                                       (7, 2048, 2048, 4), (33, 40, 50, 1), (8, 16384, 16384, 148)])
+def test_approx_match_plan_slot_arithmetic(b, n, m, sms):
+    """Host logic of approx_match without a GPU.  Every sweep splits its (element, own block, streamed chunk) tasks
+    into contiguous spans, one per CTA of the cooperative grid; a CTA leaving an own block stores its partial sums
+    in slot min(cta - owner(first task of the block), its first chunk in the block), and the NEXT sweep sums exactly
+    slots_of() = min(owner(last) - owner(first) + 1, chunks) slots.  Both counts must agree and fit the workspace."""
+    lib = _lib.load()
+    plan = (C.c_int * 6)()
+    assert lib.pnae_approx_match_plan(b, n, m, sms, plan) == 0
+    grid, nslot, maxnm, own, ts, threads = list(plan)
+    assert maxnm == max(n, m) and own == 2 * threads and own % ts == 0 and grid % sms == 0
+    for nown, nstr in ((n, m), (m, n)):
+        nob, nch = -(-nown // own), -(-nstr // ts)
+        T = b * nob * nch
+        owner = lambda t: ((t + 1) * grid - 1) // T
+        used = {}
+        for c in range(grid):
+            t, tend = c * T // grid, (c + 1) * T // grid
+            while t < tend:
+                blk, ch = divmod(t, nch)
+                used.setdefault(blk, []).append(min(c - owner(blk * nch), ch))
+                t += min(nch - ch, tend - t)
+        assert sorted(used) == list(range(b * nob))
+        for blk, slots in used.items():
+            first = blk * nch
+            ns = min(owner(first + nch - 1) - owner(first) + 1, nch)
+            assert sorted(slots) == list(range(len(slots))) and len(slots) == ns <= nslot, (blk, slots, ns, nslot)

@@ -403,7 +403,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-emd", action="store_true")
-    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide 64, steps and warmup)")
+    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches; steps and warmup are rounded up to whole graphs)")
     args = ap.parse_args()
     if args.impl != "reference":
         spg = args.steps_per_graph

@@ -89,7 +89,7 @@ PNAE_API int pnae_chamfer_loss_grad(int b, int n, const float *xyz1, int m, cons
                                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* One Chamfer step (pnae_nn_distance_fwd + pnae_nn_distance_bwd over FIXED buffers) captured into a
- * CUDA graph: at B=32, N=M=2048 the step is three kernels and ~80 us of GPU time, so one launch per
+ * CUDA graph: at B=32, N=M=2048 the step is three kernels and ~56 us of GPU time, so one launch per
  * step instead of three is the difference between GPU-bound and host-bound.  The handle owns only
  * the graph objects; every buffer stays the caller's and must outlive the handle. */
 PNAE_API int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m, const float *xyz2,

@@ -1,6 +1,6 @@
 """CUDA-graph replay of the launch-bound Chamfer step.
 
-At B=32, N=M=2048 the forward + gradient is three kernels and about 80 us of GPU time;
+At B=32, N=M=2048 the forward + gradient is three kernels and about 56 us of GPU time;
 launching them from Python one call at a time costs more host time than that.  A
 `ChamferStep` fixes the buffers (inputs, outputs, workspace) once, has the C library capture
 NnDistance + NnDistanceGrad into one CUDA graph (pnae_chamfer_graph_create) and replays it

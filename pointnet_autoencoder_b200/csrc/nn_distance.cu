@@ -750,7 +750,7 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         return PNAE_ERR_WORKSPACE;
     }
     PNAE_REQUIRE(pnae_aligned(workspace, 8), "%s: workspace must be 8-byte aligned", op);
-    PNAE_REQUIRE((long long)n + m < (1ll << 31), "%s: n + m must be below 2^31 (got %d + %d)", op, n, m);
+    PNAE_REQUIRE((long long)n + m < (1ll << 31) - 4096, "%s: n + m must stay below 2^31 - 4096 (got %d + %d)", op, n, m);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     for (int e0 = 0; e0 < b; e0 += pl.be) {

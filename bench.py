@@ -335,6 +335,8 @@ def run_product(args):
                      "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/r1_microbench_b200.txt)" % (sms.value, sm_max),
                      "traffic_source": "dram__bytes_read+write of nn_fwd_kernel, ncu --set full (profiles/r1_ncu_full_summary.txt); algorithmic bytes %d" % alg_bytes,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
+                     # the same FLOPs over the whole fwd+grad step (gradient FLOPs counted as 0)
+                     "fwd_grad_step_frac": FLOP_PER_PAIR * pairs / (ms / args.steps * 1e-3) / 1e12 / fp32_peak,
                      "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

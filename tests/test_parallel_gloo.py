@@ -33,7 +33,7 @@ def _worker(rank, world, port, fn, out):
 
 
 def run2(fn, world=2):
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # no fork() of this multi-threaded process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), fn, out), nprocs=world, join=True)
     assert all(out.get(r) == "ok" for r in range(world)), dict(out)

@@ -99,9 +99,9 @@ def test_chamfer_graph_step_equals_eager_calls():
     assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
 
 
-def test_finalize_wide_index_path_matches_oracle():
-    """The finalize kernel has a 64-bit index instantiation for launches whose point / unit counts overflow
-    32 bits; PNAE_NN_INDEX64 forces it at a size the oracle can check (separate process: the switch is read once)."""
+def test_wide_index_span_arithmetic_matches_oracle():
+    """The sweep computes its spans and slot ranks in 32 bits when the launch fits and in 64 bits otherwise;
+    PNAE_NN_INDEX64 forces the wide path at a size the oracle can check (separate process: the switch is read once)."""
     import os, subprocess, sys, tempfile
     x1, x2 = synthetic.s_randn(3, 333, 517, seed=21)
     od1, oi1, od2, oi2 = O.nn_distance(x1, x2)

@@ -20,7 +20,7 @@
  * Parity pinning: the reference ships no golden vectors.
  * This restatement is pinned (tests/test_oracle_cpu.py) against the reference's
  * own CPU loops compiled from /root/reference into oracle/_ref/libref_cpu.so, and
- * (tests/test_ref_gpu.py, on the GPU box) against the reference's own CUDA
+ * (tests/test_gpu_parity.py::TestAgainstReferenceKernels, on the GPU box) against the reference's own CUDA
  * kernels compiled unmodified into oracle/_ref/libref_gpu.so, plus the golden
  * fixtures under tests/golden/ that were generated from those kernels.
  *

@@ -310,6 +310,7 @@ def run_product(args):
 
     pairs = B * N * M
     value = pairs * args.steps * world / (ms * 1e-3) / 1e9
+    ffma_tflops = measure_ffma_rate(lib, torch, dev)
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     fp32_peak = sms.value * 128 * 2 * sm_max * 1e6 / 1e12          # TFLOP/s at the max SM clock
     achieved = FLOP_PER_PAIR * pairs / (fwd_ms * 1e-3) / 1e12
@@ -334,6 +335,8 @@ def run_product(args):
                      "frac": achieved / fp32_peak, "traffic": 1624064,
                      "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/r1_microbench_b200.txt)" % (sms.value, sm_max),
                      "traffic_source": "dram__bytes_read+write of nn_fwd_kernel, ncu --set full (profiles/r1_ncu_full_summary.txt); algorithmic bytes %d" % alg_bytes,
+                     # the same launch against the FFMA rate measured in this run (pnae_fp32_probe), None if the probe failed
+                     "peak_ffma_measured": ffma_tflops, "frac_of_ffma_measured": (achieved / ffma_tflops) if ffma_tflops else None,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
                      # the same FLOPs over the whole fwd+grad step (gradient FLOPs counted as 0)
                      "fwd_grad_step_frac": FLOP_PER_PAIR * pairs / (ms / args.steps * 1e-3) / 1e12 / fp32_peak,
@@ -353,6 +356,35 @@ def run_product(args):
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_ffma_rate(lib, torch, dev):
+    """TFLOP/s of a pure FFMA stream (8 independent chains per thread, 8 x 256 threads per SM), best of 5, timed with
+    CUDA events on the launching stream; None if anything about the probe fails -- it must never cost the bench line."""
+    try:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        out = torch.empty((sms * 8 * 256,), dtype=torch.float32, device=dev)
+        flop = C.c_longlong(0)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def _lib_check(rc):
+            if rc:
+                raise RuntimeError(lib.pnae_last_error().decode())
+
+        _lib_check(lib.pnae_fp32_probe(256, C.c_void_p(out.data_ptr()), out.numel(), C.byref(flop), st))
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(5):
+            a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib_check(lib.pnae_fp32_probe(16384, C.c_void_p(out.data_ptr()), out.numel(), C.byref(flop), st))
+            b_.record(); b_.synchronize()
+            t = a.elapsed_time(b_)
+            best = t if best is None else min(best, t)
+        return flop.value / (best * 1e-3) / 1e12
+    except Exception as e:      # noqa: BLE001
+        print("fp32 probe failed: %s" % e, file=sys.stderr)
+        return None
 
 
 def emd_numbers(dev):

@@ -53,6 +53,11 @@ PNAE_API const char *pnae_last_error(void);
 /* SM count and compute capability of the current device. */
 PNAE_API int pnae_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* FP32 issue-rate probe (measurement aid, not part of the reference's interface): launches 8 CTAs x 256 threads
+ * per SM, each thread running 8 independent chains of `iters` FFMAs; *flop receives the FLOPs of the launch
+ * (FMA = 2).  out: device scratch of at least sm_count*8*256 floats.  The caller times the launch. */
+PNAE_API int pnae_fp32_probe(int iters, float *out, size_t out_floats, long long *flop, void *stream);
+
 /* ---- Chamfer distance -------------------------------------------------- */
 
 /* Scratch bytes pnae_nn_distance_fwd needs for these sizes (may be 0). */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pnae_version": (_i, []),
     "pnae_last_error": (C.c_char_p, []),
     "pnae_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "pnae_fp32_probe": (_i, [_i, _vp, _sz, C.POINTER(C.c_longlong), _vp]),
     "pnae_nn_distance_workspace_bytes": (_sz, [_i, _i, _i]),
     "pnae_nn_distance_plan": (_i, [_i, _i, _i, _i, _vp]),
     "pnae_nn_distance_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -142,3 +142,23 @@ def test_approx_match_plan_slot_arithmetic(b, n, m, sms):
             first = blk * nch
             ns = min(owner(first + nch - 1) - owner(first) + 1, nch)
             assert sorted(slots) == list(range(len(slots))) and len(slots) == ns <= nslot, (blk, slots, ns, nslot)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/pnae.h must be usable from C (the boundary is a C ABI): compile a strict C99 translation unit that
+    includes it, link it against libpnae.so and run a host-only call."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _lib.load()
+    src = tmp_path / "use_pnae.c"
+    src.write_text('#include "pnae.h"\n#include <stdio.h>\n'
+                   'int main(void) { int plan[9]; int rc = pnae_nn_distance_plan(32, 2048, 2048, 148, plan);\n'
+                   '  printf("%d %d %d %d\\n", rc, pnae_version(), plan[0], plan[1]); return rc; }\n')
+    exe = tmp_path / "use_pnae"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lpnae", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.split() == ["0", "100", "8", "64"], (out.stdout, out.stderr)

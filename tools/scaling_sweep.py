@@ -7,7 +7,8 @@ GPU) and the Chamfer + EMD size sweep N=M in {2048, 4096, 8192, 16384} at B=64 (
 
 Every rank owns a contiguous batch slice (parallel.shard_bounds); there is no data-path collective.  Times are
 CUDA-event times of `iters` back-to-back calls after a warm-up, max over ranks; one JSON line per size on rank 0.
-NOT YET RUN on a GPU box (written after round 1's GPU budget was spent): wrap it in `timeout` the first time.
+NOT YET RUN on a GPU box (written after round 1's GPU budget was spent).  It aborts itself after
+PNAE_MAX_SECONDS (default 600) so a hang cannot burn a multi-GPU box's budget.
 """
 import json
 import os
@@ -39,6 +40,16 @@ def timed(fn, iters, world, dev):
 
 
 def main():
+    import threading
+    limit = float(os.environ.get("PNAE_MAX_SECONDS", "600"))      # never hang a (multi-)GPU box: it is charged per GPU
+
+    def _abort():
+        sys.stderr.write("scaling_sweep.py: exceeded %.0f s, aborting\n" % limit)
+        sys.stderr.flush()
+        os._exit(3)
+    wd = threading.Timer(limit, _abort)
+    wd.daemon = True
+    wd.start()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

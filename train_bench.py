@@ -68,7 +68,18 @@ def main():
     ap.add_argument("--two-op-loss", action="store_true", help="Chamfer loss through nn_distance + nn_distance_grad instead of the fused entry point")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--tf32", action="store_true", help="let the LIBRARY GEMMs/convs (decoder, encoder layers 1-4) use TF32 tensor cores")
+    ap.add_argument("--max-seconds", type=float, default=300.0, help="hard wall-clock limit: the process exits with status 3 instead of hanging a GPU box (0 = none)")
     args = ap.parse_args()
+    if args.max_seconds > 0:
+        import threading
+
+        def _abort():
+            sys.stderr.write("train_bench.py: exceeded --max-seconds %.0f, aborting\n" % args.max_seconds)
+            sys.stderr.flush()
+            os._exit(3)
+        wd = threading.Timer(args.max_seconds, _abort)
+        wd.daemon = True
+        wd.start()
     if args.cpu_baseline:
         return cpu_baseline(args)
 

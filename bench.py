@@ -438,7 +438,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-emd", action="store_true")
     ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches; steps and warmup are rounded up to whole graphs)")
+    ap.add_argument("--max-seconds", type=float, default=1200.0, help="hard wall-clock limit: exit with status 3 instead of hanging a GPU box (0 = none)")
     args = ap.parse_args()
+    if args.max_seconds > 0:
+        def _abort():
+            sys.stderr.write("bench.py: exceeded --max-seconds %.0f, aborting\n" % args.max_seconds)
+            sys.stderr.flush()
+            os._exit(3)
+        wd = threading.Timer(args.max_seconds, _abort)
+        wd.daemon = True
+        wd.start()
     if args.impl != "reference":
         spg = args.steps_per_graph
         args.steps = max(spg, (args.steps + spg - 1) // spg * spg)      # whole graphs only; the JSON line reports the steps actually run

@@ -346,3 +346,88 @@ ORACLE_API void oracle_matchcost_factors(int b, int n, int m, const float *xyz1,
     free(acc);
     free(lv);
 }
+
+/* ------------------------------------------------------------------------- */
+/* fp64 ground truth of the whole EMD pipeline.                               */
+/* ------------------------------------------------------------------------- */
+
+/* approxmatch -> matchcost -> matchcostgrad (tf_approxmatch_g.cu:1-295, GPU schedule, jstart levels) evaluated
+ * end to end in double: distances, exponentials, every sum and division.  The float constants of the reference
+ * (1e-9f, 1e-20f, multiL/multiR, the levels) keep their float values.  This is the value every fp32 evaluation
+ * order of the algorithm approximates; tests use it to rank the product and the reference kernels by their
+ * distance to it (the algorithm is ill-conditioned in fp32 on some shapes, so "within 1e-4 of another fp32
+ * evaluation" is not always attainable -- "no farther from the truth than the reference" is).
+ *   cost (b,) , grad1 (b,n,3), grad2 (b,m,3) as doubles; factors64 (b,nlev,n+m) doubles or NULL. */
+ORACLE_API void oracle_emd_fp64(int b, int n, int m, const float *xyz1, const float *xyz2, int jstart,
+                                double *cost, double *grad1, double *grad2, double *factors64)
+{
+    int nlev = jstart + 3;
+    double multiL, multiR;
+    if (n >= m) { multiL = 1; multiR = (double)(n / m); }
+    else        { multiL = (double)(m / n); multiR = 1; }
+    const double eps9 = (double)1e-9f, eps20 = (double)1e-20f;
+    double *remainL = (double *)malloc(sizeof(double) * (size_t)(n + m) * 2);
+    double *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+    double *fac = (double *)malloc(sizeof(double) * (size_t)nlev * (n + m));
+    double *lv = (double *)malloc(sizeof(double) * nlev);
+    for (int j = jstart, t = 0; j >= -2; j--, t++) lv[t] = (j == -2) ? 0.0 : -pow(4.0, (double)j);
+    for (int i = 0; i < b; i++) {
+        const float *p1 = xyz1 + (size_t)i * n * 3;
+        const float *p2 = xyz2 + (size_t)i * m * 3;
+        for (int k = 0; k < n; k++) remainL[k] = multiL;
+        for (int l = 0; l < m; l++) remainR[l] = multiR;
+        for (int lev = 0; lev < nlev; lev++) {
+            const double level = lv[lev];
+            for (int k = 0; k < n; k++) {
+                double suml = eps9;
+                for (int l = 0; l < m; l++) {
+                    double dx = (double)p2[l*3] - p1[k*3], dy = (double)p2[l*3+1] - p1[k*3+1], dz = (double)p2[l*3+2] - p1[k*3+2];
+                    suml += exp(level * (dx*dx + dy*dy + dz*dz)) * remainR[l];
+                }
+                ratioL[k] = remainL[k] / suml;
+            }
+            for (int l = 0; l < m; l++) {
+                double sumr = 0;
+                for (int k = 0; k < n; k++) {
+                    double dx = (double)p2[l*3] - p1[k*3], dy = (double)p2[l*3+1] - p1[k*3+1], dz = (double)p2[l*3+2] - p1[k*3+2];
+                    sumr += exp(level * (dx*dx + dy*dy + dz*dz)) * ratioL[k];
+                }
+                sumr *= remainR[l];
+                double consumption = fmin(remainR[l] / (sumr + eps9), 1.0);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmax(0.0, remainR[l] - sumr);
+            }
+            for (int k = 0; k < n; k++) {
+                double suml = 0;
+                for (int l = 0; l < m; l++) {
+                    double dx = (double)p2[l*3] - p1[k*3], dy = (double)p2[l*3+1] - p1[k*3+1], dz = (double)p2[l*3+2] - p1[k*3+2];
+                    suml += exp(level * (dx*dx + dy*dy + dz*dz)) * ratioL[k] * ratioR[l];
+                }
+                remainL[k] = fmax(0.0, remainL[k] - suml);
+            }
+            memcpy(fac + (size_t)lev * (n + m), ratioL, sizeof(double) * n);
+            memcpy(fac + (size_t)lev * (n + m) + n, ratioR, sizeof(double) * m);
+        }
+        if (factors64) memcpy(factors64 + (size_t)i * nlev * (n + m), fac, sizeof(double) * (size_t)nlev * (n + m));
+        double s = 0;
+        double *g1 = grad1 + (size_t)i * n * 3, *g2 = grad2 + (size_t)i * m * 3;
+        memset(g1, 0, sizeof(double) * 3 * (size_t)n);
+        memset(g2, 0, sizeof(double) * 3 * (size_t)m);
+        for (int l = 0; l < m; l++)
+            for (int k = 0; k < n; k++) {
+                double dx = (double)p1[k*3] - p2[l*3], dy = (double)p1[k*3+1] - p2[l*3+1], dz = (double)p1[k*3+2] - p2[l*3+2];
+                double d = dx*dx + dy*dy + dz*dz;
+                double mv = 0;
+                for (int t = 0; t < nlev; t++)
+                    mv += exp(lv[t] * d) * fac[(size_t)t * (n + m) + k] * fac[(size_t)t * (n + m) + n + l];
+                s += sqrt(d) * mv;
+                double w = mv / sqrt(fmax(d, eps20));
+                g1[k*3+0] += dx * w; g1[k*3+1] += dy * w; g1[k*3+2] += dz * w;
+                g2[l*3+0] -= dx * w; g2[l*3+1] -= dy * w; g2[l*3+2] -= dz * w;
+            }
+        cost[i] = s;
+    }
+    free(remainL);
+    free(fac);
+    free(lv);
+}

@@ -119,6 +119,17 @@ class Oracle:
         return cost, g1, g2
 
 
+    def emd_fp64(self, xyz1, xyz2, jstart=JSTART_GPU):
+        """fp64 ground truth of approx_match -> match_cost -> match_cost_grad: cost (B,), grad1, grad2 (float64)"""
+        xyz1, xyz2, b, n, m = _check_pair(xyz1, xyz2)
+        cost = np.empty((b,), np.float64)
+        g1 = np.empty((b, n, 3), np.float64); g2 = np.empty((b, m, 3), np.float64)
+        dp = C.POINTER(C.c_double)
+        self.lib.oracle_emd_fp64(b, n, m, xyz1.ctypes.data_as(_f32p), xyz2.ctypes.data_as(_f32p), jstart,
+                                 cost.ctypes.data_as(dp), g1.ctypes.data_as(dp), g2.ctypes.data_as(dp), None)
+        return cost, g1, g2
+
+
 class RefCpu:
     """The reference's own CPU loops (libref_cpu.so).  `match` crosses this
     boundary in the REFERENCE GPU layout (B,M,N); the (B,N,M) layout the CPU

@@ -96,13 +96,19 @@ def test_emd_fuzz_vs_oracle(b, n, m):
     ocost = O.match_cost(xyz1, xyz2, omatch)
     og1, og2 = O.match_cost_grad(xyz1, xyz2, omatch)
     np.testing.assert_allclose(cost.cpu().numpy(), ocost, rtol=1e-5, atol=1e-7)
-    # EMD gradients are ill-conditioned in fp32 on some shapes: the reference's own CUDA kernels sit up to 6.5e-4
-    # of the gradient scale away from the oracle (profiles/r1_emd_conditioning.txt).  Gate: never farther from the
-    # oracle than the reference kernels are (when they are on this box), and 1e-3 of scale in any case.
+    # EMD gradients are ill-conditioned in fp32 on some shapes (profiles/r1_emd_conditioning.txt: the reference's own
+    # CUDA kernels sit up to 6.5e-4 of the gradient scale away from the fp32 oracle).  The arbiter is the fp64
+    # evaluation of the whole pipeline: the product may be no farther from it than max(1e-4 (north star), the
+    # reference kernels' own distance to it).
     sc = lambda a, r: float(np.abs(a - r).max() / max(np.abs(r).max(), 1e-30))
-    e1, e2 = sc(g1.cpu().numpy(), og1), sc(g2.cpu().numpy(), og2)
-    assert e1 <= 1e-3 and e2 <= 1e-3, (e1, e2)
+    _, t1, t2 = O.emd_fp64(xyz1, xyz2)
+    e1, e2 = sc(g1.cpu().numpy(), t1), sc(g2.cpu().numpy(), t2)
+    bound1 = bound2 = 1e-4
     if oracle.ref_gpu.available() and b * n * m < 2 ** 31:
         rmatch = oracle.ref_gpu.approx_match(x1, x2)
         r1, r2 = [t.cpu().numpy() for t in oracle.ref_gpu.match_cost_grad(x1, x2, rmatch)]
-        assert e1 <= max(1e-4, 2.0 * sc(r1, og1)) and e2 <= max(1e-4, 2.0 * sc(r2, og2)), (e1, e2, sc(r1, og1), sc(r2, og2))
+        bound1 = max(bound1, sc(r1, t1)); bound2 = max(bound2, sc(r2, t2))
+    else:
+        # without the reference kernels on the box: the fp32 oracle (same schedule, sequential sums) stands in
+        bound1 = max(bound1, sc(og1, t1)); bound2 = max(bound2, sc(og2, t2))
+    assert e1 <= bound1 and e2 <= bound2, (e1, bound1, e2, bound2)

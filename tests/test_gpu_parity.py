@@ -25,6 +25,11 @@ def close_scaled(a, ref, rel, what=""):
     assert err <= rel * scale, "%s max|diff| %.3e > %.1e * max|ref| %.3e" % (what, err, rel, scale)
 
 
+def scaled_err(a, ref):
+    a = np.asarray(a, np.float64); ref = np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
 def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -308,7 +313,10 @@ class TestAgainstReferenceKernels:
         r1, r2 = oracle.ref_gpu.nn_distance_grad(x1, x2, g1, i1, g2, i2)
         assert torch.allclose(m1, r1, rtol=1e-4, atol=1e-5) and torch.allclose(m2, r2, rtol=1e-4, atol=1e-5)
 
-    @pytest.mark.parametrize("gen,b,n,m", [("chair", 4, 512, 512), ("chair", 2, 400, 100), ("chair", 2, 2048, 2048), ("randn", 2, 1024, 1024)])
+    # ("chair", 32, 2048, 2048) is the configuration BASELINE.json quotes approx_match on, ("chair", 4, 2048, 2048) its
+    # 8-GPU shard: the stream-K task split, the slot indexing and the span lengths all depend on b and on the grid
+    @pytest.mark.parametrize("gen,b,n,m", [("chair", 4, 512, 512), ("chair", 2, 400, 100), ("chair", 2, 2048, 2048), ("randn", 2, 1024, 1024),
+                                           ("chair", 32, 2048, 2048), ("chair", 4, 2048, 2048), ("chair", 16, 2048, 2048), ("randn", 8, 2048, 2048)])
     def test_emd(self, gen, b, n, m):
         xyz1, xyz2 = clouds(gen, b, n, m)
         x1 = cu(xyz1); x2 = cu(xyz2)
@@ -319,17 +327,44 @@ class TestAgainstReferenceKernels:
         scale = max(1.0, float(n) / m if n >= m else 1.0)
         # a different (chunked) summation order moves single entries by up to ~1e-4, like fp32-vs-fp64 does
         # (SURVEY section 7); the mean stays three orders of magnitude below that
-        diff = (match.dense() - rmatch).abs()
-        assert float(diff.max()) <= 5e-4 * scale and float(diff.mean()) <= 2e-7 * scale
+        dense = match.dense()
+        dense.sub_(rmatch).abs_()
+        assert float(dense.max()) <= 5e-4 * scale and float(dense.mean()) <= 2e-7 * scale
+        del dense
         cost, g1, g2 = ops.match_cost_factors(x1, x2, match.factors)
         assert torch.allclose(cost, rcost, rtol=1e-5)
-        # 1e-4 is the north-star tolerance; on the unnormalised randn clouds two fp32 evaluation orders of
-        # the SAME algorithm already differ by ~1.1e-4 of the gradient scale (single match entries move
-        # by 2e-4, see above), so that case gets 2e-4
-        gtol = 2e-4 if gen == "randn" else 1e-4
+        # Gradients: the north-star tolerance is 1e-4 of the gradient scale.  Two fp32 evaluation orders of this
+        # algorithm can differ by more than that on ill-conditioned inputs, so the arbiter is the fp64 evaluation of
+        # the whole pipeline (oracle_emd_fp64, first two batch elements): the product may not be farther from it than
+        # max(1e-4, the reference kernels' own distance to it).
+        nb = min(b, 2)
+        _, t1, t2 = O.emd_fp64(xyz1[:nb], xyz2[:nb])
+        ep = max(scaled_err(g1[:nb].cpu().numpy(), t1), scaled_err(g2[:nb].cpu().numpy(), t2))
+        er = max(scaled_err(rg1[:nb].cpu().numpy(), t1), scaled_err(rg2[:nb].cpu().numpy(), t2))
+        assert ep <= max(1e-4, er), "product %.3e from the fp64 truth, reference kernels %.3e" % (ep, er)
+        # and directly against the reference kernels, whole batch: 1e-4 wherever the reference itself is that close
+        # to the truth (otherwise the two fp32 results are each other's noise)
+        gtol = max(1e-4, 2.0 * er)
         close_scaled(g1.cpu().numpy(), rg1.cpu().numpy(), gtol, "grad1")
         close_scaled(g2.cpu().numpy(), rg2.cpu().numpy(), gtol, "grad2")
         # dense-path kernels on the reference's own match
         assert torch.allclose(ops.match_cost_dense_fwd(x1, x2, rmatch), rcost, rtol=1e-5)
         d1, d2 = ops.match_cost_dense_bwd(x1, x2, rmatch)
         assert torch.allclose(d1, rg1, rtol=1e-4, atol=2e-6) and torch.allclose(d2, rg2, rtol=1e-4, atol=2e-6)
+
+    # BASELINE.json configs[4]: N = 4096 / 8192 / 16384 at the per-GPU batch of B=64 over 8 GPUs (8), trimmed where the
+    # reference kernel's 32-bit match index (b*n*m < 2^31) or its one-CTA-per-element run time says so
+    @pytest.mark.parametrize("b,n", [(8, 4096), (2, 8192), (1, 16384)])
+    def test_sweep_sizes(self, b, n):
+        xyz1, xyz2 = clouds("chair", b, n, n)
+        x1 = cu(xyz1); x2 = cu(xyz2)
+        for a, r in zip(tf_nndistance.nn_distance(x1, x2), oracle.ref_gpu.nn_distance(x1, x2)):
+            assert torch.equal(a, r)
+        rmatch = oracle.ref_gpu.approx_match(x1, x2)
+        rcost = oracle.ref_gpu.match_cost(x1, x2, rmatch)
+        rg1, rg2 = oracle.ref_gpu.match_cost_grad(x1, x2, rmatch)
+        fac = ops.approx_match_factors(x1, x2)
+        cost, g1, g2 = ops.match_cost_factors(x1, x2, fac)
+        assert torch.allclose(cost, rcost, rtol=1e-5), (cost, rcost)
+        close_scaled(g1.cpu().numpy(), rg1.cpu().numpy(), 2e-4, "grad1")
+        close_scaled(g2.cpu().numpy(), rg2.cpu().numpy(), 2e-4, "grad2")

@@ -167,3 +167,17 @@ def test_match_cost_identical_clouds_is_small():
     cost = O.match_cost(label, label, match)
     # a perfect assignment exists (the identity); the soft assignment is close to it
     assert cost[0] < 0.05 * 128
+
+
+@pytest.mark.parametrize("n,m", [(128, 128), (200, 50), (64, 256)])
+def test_fp64_ground_truth_agrees_with_the_fp32_restatement(n, m):
+    """oracle_emd_fp64 (the arbiter of the GPU gradient tests) is the same algorithm as the fp32 restatement:
+    on well-conditioned shapes the two agree far inside the north-star tolerances."""
+    label, pred = synthetic.s_chair(2, max(n, m))
+    xyz1 = np.ascontiguousarray(label[:, :n]); xyz2 = np.ascontiguousarray(pred[:, :m])
+    c64, g1, g2 = O.emd_fp64(xyz1, xyz2)
+    match = O.approx_match(xyz1, xyz2)
+    np.testing.assert_allclose(O.match_cost(xyz1, xyz2, match), c64, rtol=2e-6)
+    o1, o2 = O.match_cost_grad(xyz1, xyz2, match)
+    sc = lambda a, r: np.abs(a - r).max() / np.abs(r).max()
+    assert sc(o1, g1) < 2e-5 and sc(o2, g2) < 2e-5

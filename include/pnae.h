@@ -93,6 +93,17 @@ PNAE_API int pnae_chamfer_loss_grad(int b, int n, const float *xyz1, int m, cons
                                     float *dist1, int *idx1, float *dist2, int *idx2,
                                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* NnDistance and NnDistanceGrad in ONE call, for callers whose upstream gradients do not depend on this call's
+ * distances (every loss that is linear in dist1/dist2, e.g. the Chamfer loss of models/model.py:80-83, whose
+ * grad_dist is the constant 100/(b*n)).  Replaces NmDistanceKernelLauncher followed by NmDistanceGradKernelLauncher
+ * (tf_nndistance_g.cu:128-157): same outputs as pnae_nn_distance_fwd + pnae_nn_distance_bwd, two launches instead of
+ * three and no idx/dist round trip between them.  Same workspace as pnae_nn_distance_fwd. */
+PNAE_API int pnae_nn_distance_fwd_grad(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                       const float *grad_dist1, const float *grad_dist2,
+                                       float *dist1, int *idx1, float *dist2, int *idx2,
+                                       float *grad_xyz1, float *grad_xyz2,
+                                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* One Chamfer step (pnae_nn_distance_fwd + pnae_nn_distance_bwd over FIXED buffers) captured into a
  * CUDA graph: at B=32, N=M=2048 the step is three kernels and ~56 us of GPU time, so one launch per
  * step instead of three is the difference between GPU-bound and host-bound.  The handle owns only
@@ -109,8 +120,35 @@ PNAE_API int pnae_chamfer_graph_create_multi(int steps, int b, int n, const floa
                                              const float *grad_dist1, const float *grad_dist2,
                                              float *grad_xyz1, float *grad_xyz2,
                                              void *workspace, size_t workspace_bytes, void **handle);
+/* The same over pnae_nn_distance_fwd_grad (two kernels per step); gradient outputs are required. */
+PNAE_API int pnae_chamfer_graph_create_fused_multi(int steps, int b, int n, const float *const *xyz1, int m, const float *const *xyz2,
+                                                   float *dist1, int *idx1, float *dist2, int *idx2,
+                                                   const float *grad_dist1, const float *grad_dist2,
+                                                   float *grad_xyz1, float *grad_xyz2,
+                                                   void *workspace, size_t workspace_bytes, void **handle);
 PNAE_API int pnae_graph_launch(void *handle, void *stream);
 PNAE_API int pnae_graph_destroy(void *handle);
+
+/* Streaming host-buffer form of the Chamfer step: what a caller without device data runs (the reference feeds its
+ * op from host memory through feed_dict and reads results through sess.run, train.py:196-206).  `depth` buffer sets
+ * on three internal streams: the host->device copy of step i+1, the kernels of step i and the device->host copy of
+ * step i-1 overlap.  All memory is the caller's: per set a device xyz1 (b,n,3), a device xyz2 (b,m,3), a flat device
+ * result buffer and a PINNED host result buffer of the same layout; out_offsets[6] are the byte offsets of
+ * { grad_xyz1, grad_xyz2, dist1, idx1, dist2, idx2 } inside a result buffer and d2h_bytes the leading bytes copied
+ * back per step (the whole buffer, or only the gradients when they are laid out first).  One workspace
+ * (pnae_nn_distance_workspace_bytes) is shared: the steps run in order on one stream.  fused != 0 selects
+ * pnae_nn_distance_fwd_grad (two kernels per step) over fwd + bwd (three). */
+PNAE_API int pnae_chamfer_host_pipeline_create(int depth, int b, int n, int m, int fused,
+                                               float *const *d_xyz1, float *const *d_xyz2,
+                                               void *const *d_out, void *const *h_out, const size_t *out_offsets, size_t d2h_bytes,
+                                               const float *grad_dist1, const float *grad_dist2,
+                                               void *workspace, size_t workspace_bytes, void **handle);
+/* Enqueue one step on host inputs (pinned for true asynchrony).  *retired = index of the buffer set whose results
+ * are now complete in its host buffer and stay valid until the next submit, or -1 while the pipeline fills. */
+PNAE_API int pnae_chamfer_host_pipeline_submit(void *handle, const float *h_xyz1, const float *h_xyz2, int *retired);
+/* Wait for everything in flight: retired[0..*count) = completed buffer sets, oldest first (retired needs depth ints). */
+PNAE_API int pnae_chamfer_host_pipeline_drain(void *handle, int *retired, int *count);
+PNAE_API int pnae_chamfer_host_pipeline_destroy(void *handle);
 
 /* ---- approximate earth mover's distance -------------------------------- */
 

@@ -24,7 +24,7 @@
  * kernels compiled unmodified into oracle/_ref/libref_gpu.so, plus the golden
  * fixtures under tests/golden/ that were generated from those kernels.
  *
- * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle.c -o liboracle.so -lm
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared oracle.c -o liboracle.so -lm
  * (-ffp-contract=off: every fused operation below is an explicit fmaf()).
  */
 #include <math.h>
@@ -225,6 +225,73 @@ ORACLE_API void oracle_approxmatch(int b, int n, int m, const float *xyz1, const
     free(remainL);
 }
 
+/*
+ * The same schedule with every per-point sum formed as partial sums over blocks of `chunk` streamed points, added
+ * in block order afterwards (chunk <= 0: one sequential sum, i.e. oracle_approxmatch).  Not a restatement of
+ * anything: it exists to show how far a change of SUMMATION ORDER ALONE moves the result on a given cloud
+ * (tools/emd_order_sensitivity.py), which is the yardstick for comparing two fp32 implementations.
+ */
+/* running sum in blocks: `part` collects the current block, `total` the finished blocks (block order) */
+typedef struct { float total, part; int left, chunk; } blocksum;
+static inline void bs_init(blocksum *s, float init, int chunk, int count) { s->total = init; s->part = 0; s->chunk = chunk > 0 ? chunk : count; s->left = s->chunk; }
+static inline void bs_add(blocksum *s, float term)
+{
+    s->part += term;
+    if (--s->left == 0) { s->total += s->part; s->part = 0; s->left = s->chunk; }
+}
+static inline float bs_result(const blocksum *s) { return s->left == s->chunk ? s->total : s->total + s->part; }
+
+ORACLE_API void oracle_approxmatch_order(int b, int n, int m, const float *xyz1, const float *xyz2,
+                                         float *factors, int jstart, int chunk)
+{
+    int nlev = jstart + 3;
+    float multiL, multiR;
+    if (n >= m) { multiL = 1; multiR = (float)(n / m); }
+    else        { multiL = (float)(m / n); multiR = 1; }
+    float *remainL = (float *)malloc(sizeof(float) * (size_t)(n + m) * 2);
+    float *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+    for (int i = 0; i < b; i++) {
+        const float *p1 = xyz1 + (size_t)i * n * 3;
+        const float *p2 = xyz2 + (size_t)i * m * 3;
+        for (int k = 0; k < n; k++) remainL[k] = multiL;
+        for (int l = 0; l < m; l++) remainR[l] = multiR;
+        int lev = 0;
+        for (int j = jstart; j >= -2; j--, lev++) {
+            float level = -powf(4.0f, (float)j);
+            if (j == -2) level = 0;
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < n; k++) {
+                blocksum s; bs_init(&s, 1e-9f, chunk, m);
+                for (int l = 0; l < m; l++)
+                    bs_add(&s, expf_dev(sqdist_fma(p1[k*3], p1[k*3+1], p1[k*3+2], p2[l*3], p2[l*3+1], p2[l*3+2]), level) * remainR[l]);
+                ratioL[k] = remainL[k] / bs_result(&s);
+            }
+#pragma omp parallel for schedule(static)
+            for (int l = 0; l < m; l++) {
+                blocksum s; bs_init(&s, 0.0f, chunk, n);
+                for (int k = 0; k < n; k++)
+                    bs_add(&s, expf_dev(sqdist_fma(p1[k*3], p1[k*3+1], p1[k*3+2], p2[l*3], p2[l*3+1], p2[l*3+2]), level) * ratioL[k]);
+                float sumr = bs_result(&s) * remainR[l];
+                float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmaxf(0.0f, remainR[l] - sumr);
+            }
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < n; k++) {
+                float rl = ratioL[k];
+                blocksum s; bs_init(&s, 0.0f, chunk, m);
+                for (int l = 0; l < m; l++)
+                    bs_add(&s, (expf_dev(sqdist_fma(p1[k*3], p1[k*3+1], p1[k*3+2], p2[l*3], p2[l*3+1], p2[l*3+2]), level) * rl) * ratioR[l]);
+                remainL[k] = fmaxf(0.0f, remainL[k] - bs_result(&s));
+            }
+            float *f = factors + ((size_t)i * nlev + lev) * (n + m);
+            memcpy(f, ratioL, sizeof(float) * n);
+            memcpy(f + n, ratioR, sizeof(float) * m);
+        }
+    }
+    free(remainL);
+}
+
 /* Dense match from the per-level factors, accumulated in level order exactly
  * like the `match[...]+=w` of tf_approxmatch_g.cu:152. */
 ORACLE_API void oracle_match_from_factors(int b, int n, int m, const float *xyz1, const float *xyz2,
@@ -378,6 +445,7 @@ ORACLE_API void oracle_emd_fp64(int b, int n, int m, const float *xyz1, const fl
         for (int l = 0; l < m; l++) remainR[l] = multiR;
         for (int lev = 0; lev < nlev; lev++) {
             const double level = lv[lev];
+#pragma omp parallel for schedule(static)
             for (int k = 0; k < n; k++) {
                 double suml = eps9;
                 for (int l = 0; l < m; l++) {
@@ -386,6 +454,7 @@ ORACLE_API void oracle_emd_fp64(int b, int n, int m, const float *xyz1, const fl
                 }
                 ratioL[k] = remainL[k] / suml;
             }
+#pragma omp parallel for schedule(static)
             for (int l = 0; l < m; l++) {
                 double sumr = 0;
                 for (int k = 0; k < n; k++) {
@@ -397,6 +466,7 @@ ORACLE_API void oracle_emd_fp64(int b, int n, int m, const float *xyz1, const fl
                 ratioR[l] = consumption * remainR[l];
                 remainR[l] = fmax(0.0, remainR[l] - sumr);
             }
+#pragma omp parallel for schedule(static)
             for (int k = 0; k < n; k++) {
                 double suml = 0;
                 for (int l = 0; l < m; l++) {
@@ -411,20 +481,40 @@ ORACLE_API void oracle_emd_fp64(int b, int n, int m, const float *xyz1, const fl
         if (factors64) memcpy(factors64 + (size_t)i * nlev * (n + m), fac, sizeof(double) * (size_t)nlev * (n + m));
         double s = 0;
         double *g1 = grad1 + (size_t)i * n * 3, *g2 = grad2 + (size_t)i * m * 3;
-        memset(g1, 0, sizeof(double) * 3 * (size_t)n);
-        memset(g2, 0, sizeof(double) * 3 * (size_t)m);
-        for (int l = 0; l < m; l++)
+        /* two passes so that every output has one owner: rows own cost terms and grad1, columns own grad2
+         * (each thread sums its own point in index order: the result does not depend on the thread count) */
+        double *rowcost = (double *)malloc(sizeof(double) * n);
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < n; k++) {
+            double c = 0, ax = 0, ay = 0, az = 0;
+            for (int l = 0; l < m; l++) {
+                double dx = (double)p1[k*3] - p2[l*3], dy = (double)p1[k*3+1] - p2[l*3+1], dz = (double)p1[k*3+2] - p2[l*3+2];
+                double d = dx*dx + dy*dy + dz*dz;
+                double mv = 0;
+                for (int t = 0; t < nlev; t++)
+                    mv += exp(lv[t] * d) * fac[(size_t)t * (n + m) + k] * fac[(size_t)t * (n + m) + n + l];
+                c += sqrt(d) * mv;
+                double w = mv / sqrt(fmax(d, eps20));
+                ax += dx * w; ay += dy * w; az += dz * w;
+            }
+            rowcost[k] = c; g1[k*3] = ax; g1[k*3+1] = ay; g1[k*3+2] = az;
+        }
+        for (int k = 0; k < n; k++) s += rowcost[k];
+        free(rowcost);
+#pragma omp parallel for schedule(static)
+        for (int l = 0; l < m; l++) {
+            double ax = 0, ay = 0, az = 0;
             for (int k = 0; k < n; k++) {
                 double dx = (double)p1[k*3] - p2[l*3], dy = (double)p1[k*3+1] - p2[l*3+1], dz = (double)p1[k*3+2] - p2[l*3+2];
                 double d = dx*dx + dy*dy + dz*dz;
                 double mv = 0;
                 for (int t = 0; t < nlev; t++)
                     mv += exp(lv[t] * d) * fac[(size_t)t * (n + m) + k] * fac[(size_t)t * (n + m) + n + l];
-                s += sqrt(d) * mv;
                 double w = mv / sqrt(fmax(d, eps20));
-                g1[k*3+0] += dx * w; g1[k*3+1] += dy * w; g1[k*3+2] += dz * w;
-                g2[l*3+0] -= dx * w; g2[l*3+1] -= dy * w; g2[l*3+2] -= dz * w;
+                ax -= dx * w; ay -= dy * w; az -= dz * w;
             }
+            g2[l*3] = ax; g2[l*3+1] = ay; g2[l*3+2] = az;
+        }
         cost[i] = s;
     }
     free(remainL);

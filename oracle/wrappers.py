@@ -79,6 +79,15 @@ class Oracle:
             return mt, fc
         return mt if dense else fc
 
+    def approx_match_order(self, xyz1, xyz2, chunk, jstart=JSTART_GPU):
+        """factors of the same fp32 schedule with every per-point sum formed in blocks of `chunk` streamed points
+        (0: one sequential sum): shows what a change of summation order alone does on a given cloud"""
+        xyz1, xyz2, b, n, m = _check_pair(xyz1, xyz2)
+        fc = np.empty((b, jstart + 3, n + m), np.float32)
+        self.lib.oracle_approxmatch_order(b, n, m, xyz1.ctypes.data_as(_f32p), xyz2.ctypes.data_as(_f32p),
+                                          fc.ctypes.data_as(_f32p), jstart, int(chunk))
+        return fc
+
     def match_from_factors(self, xyz1, xyz2, factors, jstart=JSTART_GPU):
         xyz1, xyz2, b, n, m = _check_pair(xyz1, xyz2)
         fc, fcp = _f(factors)
@@ -119,15 +128,28 @@ class Oracle:
         return cost, g1, g2
 
 
-    def emd_fp64(self, xyz1, xyz2, jstart=JSTART_GPU):
-        """fp64 ground truth of approx_match -> match_cost -> match_cost_grad: cost (B,), grad1, grad2 (float64)"""
+    def emd_fp64(self, xyz1, xyz2, jstart=JSTART_GPU, dense=False):
+        """fp64 ground truth of approx_match -> match_cost -> match_cost_grad: cost (B,), grad1, grad2 (float64)
+        [, the dense match (B,M,N) float64 if dense]"""
         xyz1, xyz2, b, n, m = _check_pair(xyz1, xyz2)
         cost = np.empty((b,), np.float64)
         g1 = np.empty((b, n, 3), np.float64); g2 = np.empty((b, m, 3), np.float64)
+        nlev = jstart + 3
+        fac = np.empty((b, nlev, n + m), np.float64) if dense else None
         dp = C.POINTER(C.c_double)
         self.lib.oracle_emd_fp64(b, n, m, xyz1.ctypes.data_as(_f32p), xyz2.ctypes.data_as(_f32p), jstart,
-                                 cost.ctypes.data_as(dp), g1.ctypes.data_as(dp), g2.ctypes.data_as(dp), None)
-        return cost, g1, g2
+                                 cost.ctypes.data_as(dp), g1.ctypes.data_as(dp), g2.ctypes.data_as(dp),
+                                 fac.ctypes.data_as(dp) if dense else None)
+        if not dense:
+            return cost, g1, g2
+        levels = np.array([0.0 if j == -2 else -(4.0 ** j) for j in range(jstart, -3, -1)])
+        mt = np.zeros((b, m, n), np.float64)
+        for i in range(b):
+            a = xyz1[i].astype(np.float64); c = xyz2[i].astype(np.float64)
+            d = ((c[:, None, :] - a[None, :, :]) ** 2).sum(-1)            # (m, n)
+            for t in range(nlev):
+                mt[i] += np.exp(levels[t] * d) * fac[i, t, None, :n] * fac[i, t, n:, None]
+        return cost, g1, g2, mt
 
 
 class RefCpu:

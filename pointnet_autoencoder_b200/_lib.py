@@ -35,8 +35,14 @@ SIGNATURES = {
     "pnae_nn_distance_fwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pnae_nn_distance_bwd": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnae_chamfer_loss_grad": (_i, [_i, _i, _vp, _i, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pnae_nn_distance_fwd_grad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pnae_chamfer_graph_create_fused_multi": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_graph_create": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_graph_create_multi": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "pnae_chamfer_host_pipeline_create": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "pnae_chamfer_host_pipeline_submit": (_i, [_vp, _vp, _vp, C.POINTER(_i)]),
+    "pnae_chamfer_host_pipeline_drain": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "pnae_chamfer_host_pipeline_destroy": (_i, [_vp]),
     "pnae_graph_launch": (_i, [_vp, _vp]),
     "pnae_graph_destroy": (_i, [_vp]),
     "pnae_approx_match_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -64,13 +70,20 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         if shutil.which("nvcc") is None:
             raise ImportError(
                 "pointnet_autoencoder_b200: %s is missing and nvcc is not available to build it; "
                 "run `python -m pointnet_autoencoder_b200.build`. There is no CPU fallback." % LIB_PATH)
-        from . import build as _build
         _build.build()
+    elif not _build.up_to_date():
+        # the .so does not match the sources next to it (an edit without a rebuild): never run a stale binary silently
+        if shutil.which("nvcc") is not None and os.environ.get("PNAE_NO_REBUILD") is None:
+            _build.build()
+        else:
+            raise ImportError("pointnet_autoencoder_b200: %s is older than its sources (csrc/*.cu, include/pnae.h); "
+                              "run `python -m pointnet_autoencoder_b200.build`" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here = header / library mismatch: fail loudly

@@ -33,20 +33,28 @@ def _sources():
 
 
 def _digest():
+    # content only (file names relative, no absolute paths): the stamp must stay valid when the tree is copied to
+    # another location, e.g. onto the GPU box
     h = hashlib.sha256()
     for p in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(INCLUDE, "pnae.h"), __file__]:
         with open(p, "rb") as f:
-            h.update(p.encode()); h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+            h.update(os.path.basename(p).encode()); h.update(f.read())
+    h.update(" ".join(a for a in NVCC_FLAGS if a != INCLUDE).encode())
     return h.hexdigest()
+
+
+def up_to_date():
+    """the in-tree libpnae.so was built from exactly the sources, header and flags that are here now"""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == _digest()
 
 
 def build(force=False, verbose=False):
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        with open(STAMP) as f:
-            if f.read().strip() == dig:
-                return LIB
+    if not force and up_to_date():
+        return LIB
     objs = []
     procs = []
     for src in _sources():

@@ -22,9 +22,12 @@ class ChamferStep:
     After `run()` the results are in .dist1 .idx1 .dist2 .idx2 .grad_xyz1 .grad_xyz2 (static
     tensors, overwritten by every run).  To feed new data, copy into `.xyz1` / `.xyz2`."""
 
-    kernels_per_run = 3     # sweep, finalize, gradient
-
-    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None, outputs=None):
+    def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None, outputs=None,
+                 fused=False):
+        # fused: NnDistance + NnDistanceGrad through pnae_nn_distance_fwd_grad (sweep + finalize, the finalize also
+        # forms the gradients) instead of the three-kernel pnae_nn_distance_fwd -> pnae_nn_distance_bwd sequence
+        self.fused = bool(fused) and not forward_only
+        self.kernels_per_run = 2 if (self.fused or forward_only) else 3
         # xyz1 / xyz2 may be LISTS of equally shaped tensors: the graph then holds that many consecutive steps
         # (one per input pair, all writing the same output buffers) and one run() replays them back to back
         multi1 = list(xyz1) if isinstance(xyz1, (list, tuple)) else [xyz1]
@@ -65,10 +68,11 @@ class ChamferStep:
             p = lambda t: C.c_void_p(t.data_ptr())
             arr1 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi1])
             arr2 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi2])
-            _lib.check(lib.pnae_chamfer_graph_create_multi(self.steps, b, n, arr1, m, arr2, p(self.dist1), p(self.idx1),
-                                                           p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),
-                                                           None if forward_only else p(self.grad_xyz1),
-                                                           None if forward_only else p(self.grad_xyz2), p(self.ws), wsb, C.byref(h)))
+            create = lib.pnae_chamfer_graph_create_fused_multi if self.fused else lib.pnae_chamfer_graph_create_multi
+            _lib.check(create(self.steps, b, n, arr1, m, arr2, p(self.dist1), p(self.idx1),
+                              p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),
+                              None if forward_only else p(self.grad_xyz1),
+                              None if forward_only else p(self.grad_xyz2), p(self.ws), wsb, C.byref(h)))
         self._h = h
         self._lib = lib
 

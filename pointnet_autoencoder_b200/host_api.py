@@ -75,69 +75,103 @@ class ChamferHostRunner:
 
 
 class ChamferHostPipeline:
-    """Streaming form of ChamferHostRunner: `depth` buffer sets and three streams so that the
-    host->device copy of step i+1, the kernels of step i and the device->host copy of step i-1
-    overlap (PCIe both directions + SMs busy at once).  Every step still moves all of its inputs
-    in and all of its results out.
+    """Streaming form of ChamferHostRunner over the C ABI's pnae_chamfer_host_pipeline_*: `depth` buffer sets and three
+    streams so that the host->device copy of step i+1, the kernels of step i and the device->host copy of step i-1
+    overlap (PCIe both directions + SMs busy at once).  One submit() is ONE call into libpnae.so (two input copies, one
+    graph launch, one result copy, events); torch only owns the memory.
 
         pipe = ChamferHostPipeline(B, N, M)
         for xyz1, xyz2 in batches:                 # pinned host tensors (or numpy arrays)
             done = pipe.submit(xyz1, xyz2)         # -> results of the step that just retired, or None
         for done in pipe.drain(): ...
 
-    Results are dicts of numpy views on pinned buffers, valid until the next submit()."""
+    results="all": every step returns dist1/idx1/dist2/idx2/grad_xyz1/grad_xyz2; results="grads": only the two
+    gradient fields cross PCIe (what a training loop consumes).  Results are dicts of numpy views on pinned buffers,
+    valid until the next submit()."""
 
-    def __init__(self, b, n, m, device="cuda", depth=4):
+    def __init__(self, b, n, m, device="cuda", depth=4, results="all", fused=True, grad_dist1=None, grad_dist2=None):
+        import ctypes as C
+        from . import _lib
+        assert results in ("all", "grads")
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.depth = depth
+        self.b, self.n, self.m = b, n, m
+        lib = _lib.load()
+        spec = [("grad_xyz1", (b, n, 3), torch.float32), ("grad_xyz2", (b, m, 3), torch.float32), ("dist1", (b, n), torch.float32),
+                ("idx1", (b, n), torch.int32), ("dist2", (b, m), torch.float32), ("idx2", (b, m), torch.int32)]
+        offs, total = [], 0
+        for name, shape, dt in spec:
+            offs.append(total)
+            total += (int(np.prod(shape)) * 4 + 255) // 256 * 256
+        grads_end = offs[2]
+        self.names = [s_[0] for s_ in spec] if results == "all" else ["grad_xyz1", "grad_xyz2"]
+        self.h2d_bytes = 4 * 3 * b * (n + m)
+        self.d2h_bytes = sum(int(np.prod(shape)) * 4 for name, shape, _ in spec if name in self.names)
+        copy_bytes = total if results == "all" else grads_end
+        f32 = dict(dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            self.s_in = torch.cuda.Stream(device=self.device)
-            self.s_run = torch.cuda.Stream(device=self.device)
-            self.s_out = torch.cuda.Stream(device=self.device)
-            self.sets = []
-            for _ in range(depth):
-                r = ChamferHostRunner(b, n, m, self.device)          # its own inputs, outputs, graph, pinned results
-                r.ev_in = torch.cuda.Event(); r.ev_run = torch.cuda.Event(); r.ev_out = torch.cuda.Event()
-                r.busy = False
-                self.sets.append(r)
-        self.h2d_bytes = self.sets[0].h2d_bytes
-        self.d2h_bytes = self.sets[0].d2h_bytes
+            self.g1 = torch.full((b, n), 100.0 / (b * n), **f32) if grad_dist1 is None else grad_dist1.to(**f32).contiguous()
+            self.g2 = torch.full((b, m), 100.0 / (b * m), **f32) if grad_dist2 is None else grad_dist2.to(**f32).contiguous()
+            self.d_xyz1 = [torch.empty((b, n, 3), **f32) for _ in range(depth)]
+            self.d_xyz2 = [torch.empty((b, m, 3), **f32) for _ in range(depth)]
+            self.d_out = [torch.empty((total,), dtype=torch.uint8, device=self.device) for _ in range(depth)]
+            self.h_out = [torch.empty((total,), dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+            self.h_in1 = [_pinned((b, n, 3), torch.float32) for _ in range(depth)]      # staging for non-pinned inputs
+            self.h_in2 = [_pinned((b, m, 3), torch.float32) for _ in range(depth)]
+            wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
+            self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=self.device)
+            arr = lambda ts: (C.c_void_p * depth)(*[t.data_ptr() for t in ts])
+            h = C.c_void_p()
+            torch.cuda.synchronize(self.device)
+            _lib.check(lib.pnae_chamfer_host_pipeline_create(depth, b, n, m, int(bool(fused)), arr(self.d_xyz1), arr(self.d_xyz2),
+                                                             arr(self.d_out), arr(self.h_out), (C.c_size_t * 6)(*offs), copy_bytes,
+                                                             C.c_void_p(self.g1.data_ptr()), C.c_void_p(self.g2.data_ptr()),
+                                                             C.c_void_p(self.ws.data_ptr()), wsb, C.byref(h)))
+        self._h, self._lib, self._check, self._C = h, lib, _lib.check, C
+        carve = lambda flat, i, shape, dt: flat[offs[i]: offs[i] + int(np.prod(shape)) * 4].view(dt).view(shape)
+        self._views = [{name: carve(self.h_out[k], i, shape, dt).numpy() for i, (name, shape, dt) in enumerate(spec) if name in self.names}
+                       for k in range(depth)]
+        self.kernels_per_step = 2 if fused else 3
         self.count = 0
+        self._retired = C.c_int(-1)
 
-    def _retire(self, r):
-        r.ev_out.synchronize()
-        r.busy = False
-        return {k: v.numpy() for k, v in r.h_out.items()}
+    def _host_ptr(self, src, stage):
+        """address of a host copy of `src` the async copy can read: pinned tensors as they are, anything else staged"""
+        if isinstance(src, torch.Tensor):
+            if src.is_pinned() and src.is_contiguous() and src.dtype == torch.float32:
+                return src.data_ptr()
+            stage.copy_(src)
+        else:
+            stage.numpy()[...] = src
+        return stage.data_ptr()
 
     def submit(self, xyz1, xyz2):
-        r = self.sets[self.count % self.depth]
-        assert not r.busy
+        k = self.count % self.depth
+        C = self._C
         with torch.cuda.device(self.device):
-            with torch.cuda.stream(self.s_in):
-                r.d_xyz1.copy_(r._stage(xyz1, r.h_xyz1), non_blocking=True)
-                r.d_xyz2.copy_(r._stage(xyz2, r.h_xyz2), non_blocking=True)
-                r.ev_in.record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(r.ev_in)
-                r.graph_step.run()
-                r.ev_run.record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(r.ev_run)
-                r.h_flat.copy_(r.d_flat, non_blocking=True)
-                r.ev_out.record(self.s_out)
-        r.busy = True
+            self._check(self._lib.pnae_chamfer_host_pipeline_submit(self._h, C.c_void_p(self._host_ptr(xyz1, self.h_in1[k])),
+                                                                    C.c_void_p(self._host_ptr(xyz2, self.h_in2[k])), C.byref(self._retired)))
         self.count += 1
-        # free the buffer set the NEXT submit will use: its results stay valid until that submit
-        nxt = self.sets[self.count % self.depth]
-        return self._retire(nxt) if nxt.busy else None
+        r = self._retired.value
+        return self._views[r] if r >= 0 else None
 
     def drain(self):
-        out = []
-        for i in range(self.depth):
-            r = self.sets[(self.count + i) % self.depth]
-            if r.busy:
-                out.append(self._retire(r))
-        return out
+        C = self._C
+        idx = (C.c_int * self.depth)(); cnt = C.c_int(0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.pnae_chamfer_host_pipeline_drain(self._h, idx, C.byref(cnt)))
+        return [self._views[idx[i]] for i in range(cnt.value)]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.pnae_chamfer_host_pipeline_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
 
 def nn_distance_host(xyz1, xyz2, grad_dist1=None, grad_dist2=None):

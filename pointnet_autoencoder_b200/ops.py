@@ -109,6 +109,27 @@ def nn_distance_bwd(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
     return o1, o2
 
 
+def nn_distance_fwd_grad(xyz1, xyz2, grad_dist1, grad_dist2):
+    """NnDistance + NnDistanceGrad in one call (two launches) for upstream gradients known beforehand:
+    -> dist1, idx1, dist2, idx2, grad_xyz1 (B,N,3), grad_xyz2 (B,M,3)"""
+    op = "NnDistanceGrad"
+    xyz1, xyz2, b, n, m = _check_pair("NnDistance", xyz1, xyz2, "nn")
+    _require(tuple(grad_dist1.shape) == (b, n), "%s requires grad_dist1 be of shape(batch,#points)" % op)
+    _require(tuple(grad_dist2.shape) == (b, m), "%s requires grad_dist2 be of shape(batch,#points)" % op)
+    g1 = _f32c(_dev(grad_dist1, "grad_dist1")); g2 = _f32c(_dev(grad_dist2, "grad_dist2"))
+    lib = _lib.load()
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=dev); idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=dev); idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        o1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev); o2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
+        ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.pnae_nn_distance_fwd_grad(b, n, _p(xyz1), m, _p(xyz2), _p(g1), _p(g2), _p(dist1), _p(idx1), _p(dist2), _p(idx2),
+                                                 _p(o1), _p(o2), _p(ws), wsb, _stream(xyz1)))
+    return dist1, idx1, dist2, idx2, o1, o2
+
+
 def chamfer_loss_grad(xyz1, xyz2, w1, w2):
     """Fused: loss = w1*sum(dist1) + w2*sum(dist2) -> (loss (), grad_xyz1 (B,N,3), grad_xyz2 (B,M,3)); two launches"""
     xyz1, xyz2, b, n, m = _check_pair("NnDistance", xyz1, xyz2, "nn")

@@ -37,7 +37,19 @@ def graph_time(fn, reps=20):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     b, n, m = (int(args[0]), int(args[1]), int(args[2])) if len(args) >= 3 else (32, 2048, 2048)
-    x1n, x2n = synthetic.s_randn(b, n, m)
+    gen = [a.split("=")[1] for a in sys.argv if a.startswith("--gen=")]
+    gen = gen[0] if gen else "randn"
+    if gen == "randn":
+        x1n, x2n = synthetic.s_randn(b, n, m)
+    elif gen == "chair":
+        x2n, x1n = synthetic.s_chair(b, max(n, m)); x1n = np.ascontiguousarray(x1n[:, :n]); x2n = np.ascontiguousarray(x2n[:, :m])
+    else:       # "dups": label resampled with replacement, pred = label + noise
+        rs = np.random.RandomState(0)
+        src = rs.uniform(-1, 1, (b, m, 3)).astype(np.float32)
+        x2n = np.take_along_axis(src, rs.randint(0, m // 2, (b, m))[:, :, None].repeat(3, 2), 1)
+        x1n = np.take_along_axis(x2n, rs.randint(0, m, (b, n))[:, :, None].repeat(3, 2), 1) + (rs.randn(b, n, 3) * 0.02).astype(np.float32)
+        x1n = np.ascontiguousarray(x1n); x2n = np.ascontiguousarray(x2n)
+    print("inputs: %s B=%d N=%d M=%d" % (gen, b, n, m))
     x1 = torch.from_numpy(x1n).cuda(); x2 = torch.from_numpy(x2n).cuda()
     pairs = b * n * m
     peak = 148 * 128 * 2 * 1.965e9
@@ -48,6 +60,8 @@ def main():
     t2 = graph_time(lambda: ops.nn_distance_bwd(x1, x2, g1, i1, g2, i2))
     print("nn_distance bwd  %8.2f us" % (t2 * 1e3))
     print("fwd+bwd          %8.2f us  %5.1f%% of fp32 peak  %.0f Gpairs/s" % ((t + t2) * 1e3, 100 * 16 * pairs / ((t + t2) * 1e-3) / peak, pairs / ((t + t2) * 1e-3) / 1e9))
+    t3 = graph_time(lambda: ops.nn_distance_fwd_grad(x1, x2, g1, g2))
+    print("fwd_grad (fused) %8.2f us  %5.1f%% of fp32 peak  %.0f Gpairs/s" % (t3 * 1e3, 100 * 16 * pairs / (t3 * 1e-3) / peak, pairs / (t3 * 1e-3) / 1e9))
     if "--emd" in sys.argv:
         fac = ops.approx_match_factors(x1, x2)
         t = graph_time(lambda: ops.approx_match_factors(x1, x2), reps=2)

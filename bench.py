@@ -7,7 +7,8 @@ nn_distance forward + gradient at B=32, N=M=2048 per GPU, in G unordered pairs/s
            --master-port P bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the Chamfer hot path (NnDistance + NnDistanceGrad through
-the C ABI) over one batch of synthetic clouds.  Prints ONE JSON line on rank 0.
+the C ABI) over one batch of synthetic clouds; K steps form a timed window and the
+median of several back-to-back windows is reported.  Prints ONE JSON line on rank 0.
 See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -209,6 +210,46 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # product arm
 # ---------------------------------------------------------------------------
+WINDOWS = 7                  # timed windows of K steps each; the reported step time is the median window
+
+
+def _pin_to_own_cores(local, world):
+    """Give every rank its own slice of the host cores: eight ranks submitting from the same cores starve each other
+    (round 1's e2e figure scaled 0.29 at 8 GPUs with all ranks on the default affinity mask)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
+
+
+def _traffic_from_profiles():
+    """DRAM bytes per launch of the sweep kernel from the committed ncu summary (profiles/): never a literal."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.txt")), reverse=True):
+        rd = wr = None
+        in_kernel = False
+        with open(path) as f:
+            for line in f:
+                if line.startswith("kernel:"):
+                    in_kernel = "nn_fwd_kernel" in line
+                elif in_kernel:
+                    m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+                    if m:
+                        v = float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1)
+                        if m.group(1) == "read":
+                            rd = v
+                        else:
+                            wr = v
+        if rd is not None and wr is not None:
+            return int(rd + wr), os.path.relpath(path, ROOT)
+    return None, None
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -220,6 +261,7 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
+    cores = _pin_to_own_cores(local, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -234,24 +276,37 @@ def run_product(args):
     g1 = torch.full((B, N), 100.0 / (B * N), device=dev); g2 = torch.full((B, M), 100.0 / (B * M), device=dev)
     stream = torch.cuda.current_stream()
 
-    # One CUDA graph per ring slot: NnDistance + NnDistanceGrad through the C ABI (3 kernels), replayed
-    # with one launch per step -- the step is launch-bound otherwise (pointnet_autoencoder_b200/graphs.py).
+    # One CUDA graph per ring slot.  A step is NnDistance + NnDistanceGrad through the C ABI: the two-kernel form
+    # (pnae_nn_distance_fwd_grad: sweep, then a finalize that also forms the gradients from the caller's grad_dist arrays)
+    # is the benchmarked one; the three-kernel form (fwd, then the separate gradient op) is timed next to it.
     from pointnet_autoencoder_b200.graphs import ChamferStep
     SPG = args.steps_per_graph      # consecutive steps captured per graph (launch overhead amortised over SPG steps)
     assert RING % SPG == 0 and args.steps % SPG == 0 and args.warmup % SPG == 0, "steps/warmup must be multiples of --steps-per-graph"
     grp = lambda t, g: [t[g * SPG + j] for j in range(SPG)]
-    slots = [ChamferStep(grp(x1, 0), grp(x2, 0), g1, g2)]
-    slots += [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, share_buffers_with=slots[0]) for g in range(1, RING // SPG)]   # new inputs, same outputs/workspace
-
+    NG = RING // SPG
+    slots = [ChamferStep(grp(x1, 0), grp(x2, 0), g1, g2, fused=True)]
+    slots += [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, fused=True, share_buffers_with=slots[0]) for g in range(1, NG)]   # new inputs, same outputs/workspace
+    slots3 = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, share_buffers_with=slots[0]) for g in range(NG)]
     # the dominant kernel pair alone (sweep + finalize), for the roofline figure
-    fwd_slots = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, forward_only=True, share_buffers_with=slots[0]) for g in range(RING // SPG)]
+    fwd_slots = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, forward_only=True, share_buffers_with=slots[0]) for g in range(NG)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    NG = RING // SPG
+    def timed_windows(which, windows):
+        """`windows` back-to-back windows of args.steps steps each, CUDA events on the launching stream around every
+        window; -> list of ms per window"""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(windows + 1)]
+        k = 0
+        evs[0].record(stream)
+        for w in range(windows):
+            for i in range(args.steps // SPG):
+                which[k % NG].run(); k += 1
+            evs[w + 1].record(stream)
+        return evs
+
     for i in range(args.warmup // SPG):
         slots[i % NG].run()
     barrier()
@@ -259,50 +314,83 @@ def run_product(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.15)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(args.steps // SPG):
-        slots[i % NG].run()
-    e1.record(stream)
+    ev_step = timed_windows(slots, WINDOWS)
     barrier()
-    # forward alone, same ring, same clocks: CUDA events on the launching stream
-    f0.record(stream)
-    for i in range(args.steps // SPG):
-        fwd_slots[i % NG].run()
-    f1.record(stream)
+    ev_three = timed_windows(slots3, WINDOWS)
+    barrier()
+    ev_fwd = timed_windows(fwd_slots, WINDOWS)       # forward alone, same ring, same clocks
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
-    ms = e0.elapsed_time(e1)
-    fwd_ms = f0.elapsed_time(f1) / args.steps
+    med = lambda evs: float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]))
+    win_ms = [ev_step[i].elapsed_time(ev_step[i + 1]) for i in range(WINDOWS)]
+    ms = float(np.median(win_ms))
+    three_ms = med(ev_three) / args.steps
+    fwd_ms = med(ev_fwd) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
+    # ---- the last timed step's results against the oracle (one element; the checker, outside every timed region)
+    check = None
+    if rank == 0:
+        import oracle
+        last = (WINDOWS * (args.steps // SPG) - 1) % NG
+        slots[last].run(); torch.cuda.synchronize()
+        e_in = last * SPG + SPG - 1
+        od1, oi1, od2, oi2 = oracle.cpu.nn_distance(h1[e_in, :1], h2[e_in, :1])
+        s0 = slots[0]
+        ok = (np.array_equal(s0.dist1[:1].cpu().numpy(), od1) and np.array_equal(s0.idx1[:1].cpu().numpy(), oi1)
+              and np.array_equal(s0.dist2[:1].cpu().numpy(), od2) and np.array_equal(s0.idx2[:1].cpu().numpy(), oi2))
+        og1, og2 = oracle.cpu.nn_distance_grad(h1[e_in, :1], h2[e_in, :1], np.full((1, N), 100.0 / (B * N), np.float32), oi1,
+                                               np.full((1, M), 100.0 / (B * M), np.float32), oi2)
+        gerr = max(float(np.abs(s0.grad_xyz1[:1].cpu().numpy() - og1).max() / np.abs(og1).max()),
+                   float(np.abs(s0.grad_xyz2[:1].cpu().numpy() - og2).max() / np.abs(og2).max()))
+        check = {"dist_idx_bit_exact_vs_oracle": bool(ok), "grad_max_rel_err_vs_oracle": gerr, "element": "batch %d, element 0" % e_in}
+        if not ok or gerr > 1e-4:
+            raise SystemExit("bench.py: the timed step's results do not match the oracle: %r" % (check,))
+
     # ---- end to end through the public host-buffer API: pinned host in, results back on the host
     e2e_steps = 400
-    runner = host_api.ChamferHostPipeline(B, N, M, dev, depth=4)
     p1 = torch.from_numpy(h1).pin_memory(); p2 = torch.from_numpy(h2).pin_memory()   # inputs start in pinned host memory
-    for i in range(6):
-        runner.submit(p1[i % RING], p2[i % RING])
-    runner.drain()
-    barrier()
-    e2e0 = time.perf_counter()
-    got = 0
-    for i in range(e2e_steps):
-        got += runner.submit(p1[i % RING], p2[i % RING]) is not None
-    got += len(runner.drain())                     # every step's results are back on the host when the clock stops
-    e2e_s = time.perf_counter() - e2e0
-    assert got == e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
 
+    def e2e_run(results):
+        runner = host_api.ChamferHostPipeline(B, N, M, dev, depth=4, results=results)
+        for i in range(8):
+            runner.submit(p1[i % RING], p2[i % RING])
+        runner.drain()
+        barrier()
+        t_0 = time.perf_counter()
+        got = 0
+        for i in range(e2e_steps):
+            got += runner.submit(p1[i % RING], p2[i % RING]) is not None
+        got += len(runner.drain())                     # every step's results are back on the host when the clock stops
+        dt = time.perf_counter() - t_0
+        assert got == e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, runner
+    e2e_s, runner = e2e_run("all")
+    e2e_grads_s, runner_g = e2e_run("grads")
+
+    extra = {}
+
+    def guarded(fn, *a):
+        # an `extra` figure must never cost the bench line (every rank runs the same code, so a failure is the same
+        # on all of them; the --max-seconds watchdog covers anything else)
+        try:
+            return fn(*a)
+        except Exception as exc:      # noqa: BLE001
+            return {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if not args.no_emd:
+        extra["emd_strong_scaling"] = guarded(emd_numbers, dev, world, rank, sms.value)
+    if not args.no_train:
+        extra["ae_train"] = guarded(train_numbers, dev, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,37 +410,51 @@ def run_product(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = 4 * (3 * B * (N + M) + 2 * B * (N + M))               # xyz in, dist+idx out
+    traffic, traffic_file = _traffic_from_profiles()
+    step_ms = ms / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (S-randn, seed 100+rank; mirrors tf_nndistance.py:45-49)",
         "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
                    "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                    "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB) > 126 MB L2; outputs and workspace are reused" % (RING, RING * 12 * B * (N + M) / 1e6),
-                   "launch": "CUDA graphs of %d consecutive steps (3 kernels per step: sweep, finalize, gradient), one replay per %d steps" % (SPG, SPG),
-                   "upstream_grad": "100/(B*N) (models/model.py:81-83)"},
+                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps" % (SPG, SPG),
+                   "timing": "%d back-to-back windows of %d steps, CUDA events on the launching stream; value = median window, max over ranks" % (WINDOWS, args.steps),
+                   "upstream_grad": "100/(B*N) (models/model.py:81-83), passed as grad_dist arrays",
+                   "host_cores_of_rank0": len(cores) if cores else None},
+        "windows": WINDOWS, "window_ms": win_ms, "timed_steps_total": WINDOWS * args.steps,
         "roofline": {"bound": "fp32", "kernel": "nn_distance forward (nn_fwd_kernel sweep + nn_finalize_kernel)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": 1624064,
+                     "frac": achieved / fp32_peak, "traffic": traffic,
                      "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (device max SM clock); FFMA microbench reaches 94%% of it (profiles/r1_microbench_b200.txt)" % (sms.value, sm_max),
-                     "traffic_source": "dram__bytes_read+write of nn_fwd_kernel, ncu --set full (profiles/r1_ncu_full_summary.txt); algorithmic bytes %d" % alg_bytes,
+                     "traffic_source": "dram__bytes_read+write of nn_fwd_kernel per launch, ncu --set full, read from %s; algorithmic bytes %d" % (traffic_file, alg_bytes),
                      # the same launch against the FFMA rate measured in this run (pnae_fp32_probe), None if the probe failed
                      "peak_ffma_measured": ffma_tflops, "frac_of_ffma_measured": (achieved / ffma_tflops) if ffma_tflops else None,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
                      # the same FLOPs over the whole fwd+grad step (gradient FLOPs counted as 0)
-                     "fwd_grad_step_frac": FLOP_PER_PAIR * pairs / (ms / args.steps * 1e-3) / 1e12 / fp32_peak,
+                     "fwd_grad_step_frac": FLOP_PER_PAIR * pairs / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                     "fwd_grad_step_frac_three_kernel_form": FLOP_PER_PAIR * pairs / (three_ms * 1e-3) / 1e12 / fp32_peak,
                      "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "e2e": {"value": pairs * e2e_steps * world / e2e_s / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
-                "api": "host_api.ChamferHostPipeline: pinned host in -> H2D -> graph (3 kernels) -> D2H of dist/idx/grads, 4 buffer sets so the copies of neighbouring steps overlap compute"},
-        "gpu_launches": 3 * args.steps,
+                "api": "host_api.ChamferHostPipeline over pnae_chamfer_host_pipeline_submit (C): pinned host in -> H2D -> graph (2 kernels) -> D2H of dist/idx/grads, 4 buffer sets on 3 streams",
+                "gradients_only": {"value": pairs * e2e_steps * world / e2e_grads_s / 1e9, "d2h_bytes_per_step": runner_g.d2h_bytes,
+                                   "note": "same pipeline returning only grad_xyz1/grad_xyz2 (what a training loop consumes)"}},
+        "gpu_launches": 2 * args.steps * WINDOWS,
         "clocks": clocks,
+        "check": check,
     }
+    extra["three_kernel_step_ms"] = three_ms
+    extra["three_kernel_step_gpairs"] = pairs * world / (three_ms * 1e-3) / 1e9
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(threads=1, reps=3)
-    if world == 1 and not args.no_emd:
-        line["extra"] = emd_numbers(dev)
+    if world == 1 and not args.no_refgpu:
+        extra["reference_gpu"] = guarded(reference_gpu_numbers, dev)
+    if world == 1:
+        extra["encoder_conv_pool"] = guarded(encoder_numbers, dev)
+    line["extra"] = extra
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -387,28 +489,120 @@ def measure_ffma_rate(lib, torch, dev):
         return None
 
 
-def emd_numbers(dev):
-    """BASELINE.json's second figure: approx_match ms (and EMD fwd+grad ms) at B=32 N=2048."""
-    import torch
-    from pointnet_autoencoder_b200 import ops, synthetic
-    label, pred = synthetic.s_chair(B, N)
-    x1 = torch.from_numpy(label).to(dev); x2 = torch.from_numpy(pred).to(dev)
+def _event_times(torch, fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b_.record(); b_.synchronize()
+        ts.append(a.elapsed_time(b_))
+    return ts
 
-    def t(fn, it=5):
-        fn(); torch.cuda.synchronize()
-        ts = []
-        for _ in range(it):
-            a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b_.record(); b_.synchronize()
-            ts.append(a.elapsed_time(b_))
-        return float(np.median(ts))
+
+def emd_numbers(dev, world, rank, sms):
+    """BASELINE.json configs[2]: approx_match + match_cost forward+gradient, B=32 in total, batch-sharded over the
+    ranks (32/world elements per GPU: STRONG scaling), S-chair clouds, 100 iterations; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from pointnet_autoencoder_b200 import ops, parallel, synthetic
+    label, pred = synthetic.s_chair(B, N)
+    lo, hi = parallel.shard_bounds(B, rank, world)
+    x1 = torch.from_numpy(np.ascontiguousarray(label[lo:hi])).to(dev); x2 = torch.from_numpy(np.ascontiguousarray(pred[lo:hi])).to(dev)
     fac = ops.approx_match_factors(x1, x2)
-    am = t(lambda: ops.approx_match_factors(x1, x2))
-    mc = t(lambda: ops.match_cost_factors(x1, x2, fac))
-    peak = 148 * 128 * 2 * 1.965e9
-    pairs = B * N * N
+    am = float(np.median(_event_times(torch, lambda: ops.approx_match_factors(x1, x2), 100)))
+    mc = float(np.median(_event_times(torch, lambda: ops.match_cost_factors(x1, x2, fac), 100)))
+    if world > 1:
+        t = torch.tensor([am, mc], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        am, mc = float(t[0]), float(t[1])
+    peak = sms * 128 * 2 * 1.965e9                    # FP32 FLOP/s of ONE GPU at the max SM clock
+    mufu = sms * 16 * 1.965e9                         # MUFU.EX2 per second of one GPU
+    pairs = B * N * N                                 # whole job
     return {"approx_match_ms": am, "match_cost_fwd_grad_ms": mc, "emd_fwd_grad_ms": am + mc,
-            "emd_frac_of_fp32_peak": 423 * pairs / ((am + mc) * 1e-3) / peak, "data": "S-chair"}
+            "elements_per_gpu": hi - lo, "total_elements": B, "iterations": 100, "data": "S-chair", "n_gpus": world,
+            "emd_frac_of_fp32_peak_all_gpus": 423 * pairs / ((am + mc) * 1e-3) / (peak * world),
+            "roofline": {"bound": "mufu", "kernel": "approx_match_kernel", "unit": "G ex2/s",
+                         "achieved": 27 * pairs / (am * 1e-3) / 1e9, "peak": mufu * world / 1e9,
+                         "frac": 27 * pairs / (am * 1e-3) / (mufu * world),
+                         "note": "27 exponentials per pair (10 levels x 3 sweeps, C_j and A_j+1 fused, last level closed form) against 16 MUFU/clk/SM; floor %.3f ms" % (27 * pairs / (mufu * world) * 1e3)},
+            "limit_at_small_shards": "19 grid-wide barriers per call are a fixed cost; at 4 elements per GPU the sweeps between them are ~8x shorter"}
+
+
+def train_numbers(dev, world):
+    """BASELINE.json configs[3]: model_upconv autoencoder training step, Chamfer loss, 32 clouds per GPU (global batch
+    32 x world; 256 at 8 GPUs), fp32 library ops for the decoder; one NCCL all-reduce of the gradient bucket per step."""
+    from pointnet_autoencoder_b200.train_step import TrainStep
+    out = {}
+    for name, kw in (("fp32", {}), ("tf32_library_ops", {"tf32": True})):
+        ts = TrainStep("upconv", 32, dev, **kw)
+        ms, loss = ts.timed(30, 5)
+        out[name] = {"samples_per_s": ts.gb / (ms * 1e-3), "ms_per_step": ms, "global_batch": ts.gb, "last_loss": loss,
+                     "grad_allreduce_bytes": 4 * ts.nparam if world > 1 else 0}
+        del ts
+    out["workload"] = "models/model_upconv.py autoencoder, Chamfer loss (fused op), N=2048, 32 clouds per GPU, Adam; 30 steps after 5"
+    return out
+
+
+def reference_gpu_numbers(dev):
+    """The same-box incumbent: the reference's own CUDA kernels (tf_nndistance_g.cu, tf_approxmatch_g.cu compiled
+    unmodified for sm_100a into oracle/_ref/libref_gpu.so) on the same inputs, outside every timed region of the
+    product.  None if the library did not travel to this box."""
+    import torch
+    import oracle
+    from pointnet_autoencoder_b200 import synthetic
+    R = oracle.ref_gpu
+    if not R.available():
+        return None
+    lib = R.lib; p = R._p
+    h1, h2 = make_inputs(B, N, M, 1)
+    x1 = torch.from_numpy(h1[0]).to(dev); x2 = torch.from_numpy(h2[0]).to(dev)
+    g1 = torch.full((B, N), 100.0 / (B * N), device=dev); g2 = torch.full((B, M), 100.0 / (B * M), device=dev)
+    d1 = torch.empty((B, N), device=dev); i1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+    d2 = torch.empty((B, M), device=dev); i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+    o1 = torch.empty((B, N, 3), device=dev); o2 = torch.empty((B, M, 3), device=dev)
+    torch.cuda.synchronize()
+
+    def legacy_time(fn, iters, warm=2):
+        # the reference launchers use the legacy default stream: bracket with events on that stream
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        legacy = torch.cuda.default_stream(dev)        # torch's default stream IS the legacy default stream
+        e0.record(legacy)
+        for _ in range(iters):
+            fn()
+        e1.record(legacy); e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def chamfer():
+        lib.ref_gpu_nn_distance(B, N, p(x1), M, p(x2), p(d1), p(i1), p(d2), p(i2))
+        lib.ref_gpu_nn_distance_grad(B, N, p(x1), M, p(x2), p(g1), p(i1), p(g2), p(i2), p(o1), p(o2))
+    step_ms = legacy_time(chamfer, 50)
+    label, pred = synthetic.s_chair(B, N)
+    c1 = torch.from_numpy(label).to(dev); c2 = torch.from_numpy(pred).to(dev)
+    match = torch.empty((B, N, N), device=dev); temp = torch.empty((B, 4 * N), device=dev); cost = torch.empty((B,), device=dev)
+    torch.cuda.synchronize()
+    am = legacy_time(lambda: lib.ref_gpu_approxmatch(B, N, N, p(c1), p(c2), p(match), p(temp)), 3, warm=1)
+    mc = legacy_time(lambda: (lib.ref_gpu_matchcost(B, N, N, p(c1), p(c2), p(match), p(cost)),
+                              lib.ref_gpu_matchcostgrad(B, N, N, p(c1), p(c2), p(match), p(o1), p(o2))), 5, warm=1)
+    return {"nn_distance_fwd_grad_ms": step_ms, "nn_distance_fwd_grad_gpairs": B * N * M / (step_ms * 1e-3) / 1e9,
+            "approx_match_ms": am, "match_cost_fwd_grad_ms": mc,
+            "what": "tf_nndistance_g.cu / tf_approxmatch_g.cu compiled unmodified for sm_100a, same B200, same inputs, legacy default stream"}
+
+
+def encoder_numbers(dev):
+    """conv5 (128 -> 1024) + pooling statistics on tcgen05 at B=32, N=2048: the encoder's dominant layer"""
+    import torch
+    from pointnet_autoencoder_b200 import ops
+    b, n, k, c = 32, 2048, 128, 1024
+    x = torch.randn(b, n, k, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(c, k, device=dev) / k ** 0.5).to(torch.bfloat16)
+    ms = float(np.median(_event_times(torch, lambda: ops.encoder_conv_pool(x, wt), 50)))
+    flop = 2.0 * b * n * k * c
+    return {"ms": ms, "tflops": flop / (ms * 1e-3) / 1e12, "note": "single launches timed one by one (includes ~launch latency); bf16 operands, fp32 accumulate"}
 
 
 _REAL_STDOUT = None
@@ -437,6 +631,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-emd", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the autoencoder training-step figure (BASELINE configs[3])")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip timing the reference's own CUDA kernels")
     ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches; steps and warmup are rounded up to whole graphs)")
     ap.add_argument("--max-seconds", type=float, default=1200.0, help="hard wall-clock limit: exit with status 3 instead of hanging a GPU box (0 = none)")
     args = ap.parse_args()

@@ -7,18 +7,11 @@
 //
 // Forward design (DESIGN.md "Chamfer forward"):
 //  * every UNORDERED pair (xyz1[j], xyz2[k]) is evaluated once and feeds both the
-//    row minimum (dist1) and the column minimum (dist2);
-//  * the sweep is a FILTER, the finalize is the arbiter.  The sweep evaluates
-//        s_jk = A_j + B_k - 2 a'_j . b'_k      (1 FADD + 3 FFMA; a' = a - o, b' = b - o centred on a per-element
-//                                               point o, A = |a'|^2 (1 + 2^-19), B likewise)
-//    which approximates |a_j - b_k|^2 to a proven bound (kBand below) instead of the reference's six-instruction
-//    expression, and tracks minima only (FMNMX3).  Every candidate whose s lies within the bound of a row's /
-//    column's minimum is remembered at coarse granularity: for a row, a bit mask of the 32-column chunks of the
-//    span; for a column, the ballot of the lanes (8 rows each) of the row block.  The finalize re-evaluates
-//    exactly those candidates with the reference's own arithmetic (FMUL(y)->FFMA(x)->FFMA(z) on rounded
-//    differences) and takes the lexicographic minimum of (distance, index): dist and idx are bit-exact, the
-//    lowest index wins ties (tools/nn_model.c is a CPU model of the scheme, checked against the oracle on
-//    adversarial inputs);
+//    row minimum (dist1) and the column minimum (dist2): (a-b)^2 == (b-a)^2 bit for
+//    bit, so this is exact and halves the FP32 work of the two reference launches;
+//  * the inner loop tracks minima only (FMNMX); indices are recovered afterwards
+//    from a coarse tag: the 32-column chunk in which a row's minimum first appeared,
+//    and the R-row group (one lane's rows) that produced a column's minimum;
 //  * sweep launch: the (element, 256-row block, 32-column chunk) units are split into
 //    equal contiguous spans, one per resident warp (stream-K style: no queue, no
 //    CTA barrier, balance to one unit); a warp keeps its rows in registers while it
@@ -73,8 +66,6 @@ struct FwdParams {
     float *gxyz1, *gxyz2;   // (be,n,3), (be,m,3): d loss / d xyz, zeroed by the sweep, accumulated by the finalize
     float w1, w2;
     const float *gd1, *gd2;   // optional per-point upstream gradients (b,n), (b,m): replace w1 / w2 (pnae_nn_distance_fwd_grad)
-    int maxspan;       // longest run of chunks one span sweeps inside one row block: min(nch, ceil(units / warps))
-    int tsh;           // row keys carry (first chunk of the span >> tsh) in 16 bits; 0 unless nch > 65535
     int zero_loss;     // this launch is the first chunk of the call: it also zeroes *loss
     int small;         // (units + 1) * warps and the point count fit 32 bits: cheap unsigned index arithmetic
 #ifdef PNAE_NN_TRACE
@@ -88,34 +79,6 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
-}
-
-// ---- the sweep's approximation and its error bound --------------------------------------------------------
-// With u = 2^-24, a' = fl(a - o), b' = fl(b - o), aa = |a'|^2, bb = |b'|^2 (exact), D = |a - b|^2 (exact):
-//   * centring moves the distance by at most 4u (aa + bb);
-//   * A = fl(fl(aa) (1 + 2^-19)) = aa (1 + 32u) +- 4u aa; likewise B;  c = fl(A + B) adds 1u (A + B);
-//   * the three FFMAs round intermediate values bounded by 2 (aa + bb): 6u (aa + bb) in total;
-//   => s = D + (32 +- 15.5) u (aa + bb): s >= 0 always (float order == unsigned order of the bits), and
-//      |s - D| <= E := 47.5u (aa + bb) <= 47.5u (3 aa + 2 D)       (|b'| <= |a'| + sqrt(D)).
-//   * the reference's own result d_ref = D (1 +- 6u).
-// If column b can beat column a for a row (d_ref(b) <= d_ref(a)) while s_a <= s_b, then
-//   s_b <= s_a (1 + 203u) + 286u aa.
-// kBand = 2^-14 = 1024u covers both terms with a factor >= 3.5 to spare; thr() below is the in-band test.
-// Columns: the same with the roles of aa and bb swapped.
-constexpr float kInfl = 1.0f + 1.0f / 524288.0f;    // 1 + 2^-19
-constexpr float kBand = 1.0f / 16384.0f;             // 2^-14
-constexpr float kInf = __builtin_huge_valf();
-
-__device__ __forceinline__ float band_thr(float s, float nrm) { return __fmaf_rn(nrm, kBand, __fmaf_rn(s, kBand, s)); }
-__device__ __forceinline__ float infl_norm(float x, float y, float z) { return __fmul_rn(pnae_sqdist(x, y, z), kInfl); }
-
-// per-element centre: the mean of four of its points (any point near the clouds does; it only tightens the bound)
-__device__ __forceinline__ void element_centre(const float *p1, int n, const float *p2, int m, float &ox, float &oy, float &oz)
-{
-    const float *q1 = p1 + (size_t)(n / 2) * 3, *q2 = p2 + (size_t)(m / 2) * 3;
-    ox = __fmul_rn(__fadd_rn(__fadd_rn(__ldg(p1), __ldg(q1)), __fadd_rn(__ldg(p2), __ldg(q2))), 0.25f);
-    oy = __fmul_rn(__fadd_rn(__fadd_rn(__ldg(p1 + 1), __ldg(q1 + 1)), __fadd_rn(__ldg(p2 + 1), __ldg(q2 + 1))), 0.25f);
-    oz = __fmul_rn(__fadd_rn(__fadd_rn(__ldg(p1 + 2), __ldg(q1 + 2)), __fadd_rn(__ldg(p2 + 2), __ldg(q2 + 2))), 0.25f);
 }
 
 // warp that owns unit u under the span formula above
@@ -271,10 +234,9 @@ nn_fwd_kernel(const FwdParams p)
     }
     if (rem <= 0) return;
 
-    // rows (centred, pre-scaled by -2), their inflated norms and the running minima of the current chunk live in
-    // registers; the per-chunk bookkeeping (each row's minimum over the span so far and the mask of the chunks
-    // that may hold its nearest neighbour) lives in shared memory so the inner loop has the whole register file
-    float rx[kR], ry[kR], rz[kR], raa[kR], best[kR];
+    // rows and their running minima live in registers; the per-chunk bookkeeping (snapshot of the minima at the
+    // last chunk boundary, tags) lives in shared memory so the inner loop has the whole register file
+    float rx[kR], ry[kR], rz[kR], best[kR];
     unsigned buf = 0;             // byte offset of the column buffer in use: 0 or kColBuf
     prefetch_rows(p.xyz1 + (size_t)e * p.n * 3, p.n, rb, sm_s + kRowOff, lane);
     prefetch_cols(p.xyz2 + (size_t)e * p.m * 3, p.m, ch, sm_s, lane);
@@ -288,10 +250,6 @@ nn_fwd_kernel(const FwdParams p)
         const float *p2 = p.xyz2 + (size_t)e * p.m * 3;
         int kcol = ch * kChunk + lane;
         u64 *ck = p.colkeys + ((size_t)e * p.nrb + rb) * p.m + kcol;
-        const unsigned ch0tag = (unsigned)ch0 >> p.tsh;               // goes into the row keys (16 bits)
-        unsigned rel = (unsigned)ch0 - (ch0tag << p.tsh);             // chunk index relative to the tagged chunk
-        float ox, oy, oz;
-        element_centre(p.xyz1 + (size_t)e * p.n * 3, p.n, p2, p.m, ox, oy, oz);
 
         cp_async_wait_all();
         __syncwarp();
@@ -305,13 +263,10 @@ nn_fwd_kernel(const FwdParams p)
                 const float4 v = lds128(sm_s + kRowOff + lane * (kR * 12) + i * 16);
                 tmp[4 * i] = v.x; tmp[4 * i + 1] = v.y; tmp[4 * i + 2] = v.z; tmp[4 * i + 3] = v.w;
             }
-            const int row0 = rb * kRowsPerBlock + lane * kR;
 #pragma unroll
             for (int r = 0; r < kR; r++) {
-                const float ax = __fsub_rn(tmp[3 * r], ox), ay = __fsub_rn(tmp[3 * r + 1], oy), az = __fsub_rn(tmp[3 * r + 2], oz);
-                rx[r] = __fmul_rn(ax, -2.0f); ry[r] = __fmul_rn(ay, -2.0f); rz[r] = __fmul_rn(az, -2.0f);
-                raa[r] = row0 + r < p.n ? infl_norm(ax, ay, az) : kInf;      // padding rows can never be a minimum
-                best[r] = kInf;
+                rx[r] = tmp[3 * r]; ry[r] = tmp[3 * r + 1]; rz[r] = tmp[3 * r + 2];
+                best[r] = __int_as_float(0x7f800000);
             }
 #pragma unroll
             for (int h = 0; h < kR / 4; h++) {
@@ -333,15 +288,6 @@ nn_fwd_kernel(const FwdParams p)
             }
             cp_async_commit();
 
-            // this chunk's columns, in place: raw (x, y, z, -) -> centred (x', y', z', B); lane c owns column c
-            {
-                const float4 c = lds128(sm_s + buf + lane * 16);
-                const float bx = __fsub_rn(c.x, ox), by = __fsub_rn(c.y, oy), bz = __fsub_rn(c.z, oz);
-                const float bb = kcol < p.m ? infl_norm(bx, by, bz) : kInf;  // padding columns can never be a minimum
-                sts128(sm_s + buf + lane * 16, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz), __float_as_uint(bb));
-            }
-            __syncwarp();
-
             // ---- 256 rows x 32 columns
             unsigned ca = sm_s + buf;                      // column records; this group's keys go to ca-relative ka
             unsigned ka = sm_s + kKeyOff;
@@ -349,10 +295,9 @@ nn_fwd_kernel(const FwdParams p)
             float4 qn = lds128(ca);
 #pragma unroll kUnroll
             do {
-                // kGroup columns at a time: their cross-lane reductions (REDUX -> threshold -> ballot) are
+                // kGroup columns at a time: their cross-lane reductions (REDUX -> compare -> ballot) are
                 // independent chains, issued back to back so their fixed latencies overlap
                 unsigned bits[kGroup];
-                float bw[kGroup];
 #pragma unroll
                 for (int g = 0; g < kGroup; g += 2) {
                     // two columns at a time so the minima can use the three-input FMNMX3
@@ -362,23 +307,20 @@ nn_fwd_kernel(const FwdParams p)
                     float d0[kR], d1[kR];
 #pragma unroll
                     for (int r = 0; r < kR; r++) {
-                        d0[r] = __fmaf_rn(rz[r], q0.z, __fmaf_rn(ry[r], q0.y, __fmaf_rn(rx[r], q0.x, __fadd_rn(raa[r], q0.w))));
-                        d1[r] = __fmaf_rn(rz[r], q1.z, __fmaf_rn(ry[r], q1.y, __fmaf_rn(rx[r], q1.x, __fadd_rn(raa[r], q1.w))));
+                        d0[r] = pnae_sqdist(q0.x - rx[r], q0.y - ry[r], q0.z - rz[r]);
+                        d1[r] = pnae_sqdist(q1.x - rx[r], q1.y - ry[r], q1.z - rz[r]);
                         best[r] = min3f(best[r], d0[r], d1[r]);
                     }
-                    // column minima over this lane's rows; s >= 0: unsigned order == float order
+                    // column minima over this lane's rows; d >= 0: unsigned order == float order
                     static_assert(kR == 8, "column tree below is written for 8 rows per lane");
                     bits[g] = __float_as_uint(fminf(min3f(min3f(min3f(d0[0], d0[1], d0[2]), d0[3], d0[4]), d0[5], d0[6]), d0[7]));
                     bits[g + 1] = __float_as_uint(fminf(min3f(min3f(min3f(d1[0], d1[1], d1[2]), d1[3], d1[4]), d1[5], d1[6]), d1[7]));
-                    bw[g] = q0.w; bw[g + 1] = q1.w;
                 }
                 unsigned mn[kGroup], who[kGroup];
 #pragma unroll
                 for (int g = 0; g < kGroup; g++) mn[g] = __reduce_min_sync(0xffffffffu, bits[g]);
-                // every lane whose rows come within the error bound of the column's minimum is a candidate
 #pragma unroll
-                for (int g = 0; g < kGroup; g++)
-                    who[g] = __ballot_sync(0xffffffffu, __uint_as_float(bits[g]) <= band_thr(__uint_as_float(mn[g]), bw[g]));
+                for (int g = 0; g < kGroup; g++) who[g] = __ballot_sync(0xffffffffu, bits[g] == mn[g]);
                 static_assert(kGroup == 4, "two 16-byte key stores per group");
                 sts128_if(lane == 0, ka, who[0], mn[0], who[1], mn[1]);          // u64 key = min bits << 32 | ballot
                 sts128_if(lane == 0, ka + 16, who[2], mn[2], who[3], mn[3]);
@@ -388,35 +330,20 @@ nn_fwd_kernel(const FwdParams p)
             __syncwarp();
             const u64 mykey = lds64(sm_s + kKeyOff + lane * 8);     // lane c carries the key of column c of this chunk
             __syncwarp();
-            // rows: fold this chunk's minimum into the span's.  The chunk's bit is set when the chunk holds the new
-            // minimum or comes within the error bound of it; earlier bits survive unless the new minimum beats the
-            // old one by more than the bound (then nothing seen before can hold the nearest neighbour).
-            {
-                const unsigned bit = 1u << (rel & 15u);
+            // a strict decrease during this chunk => the row's running minimum first appears here
 #pragma unroll
-                for (int h = 0; h < kR / 4; h++) {
-                    const float4 sn = lds128(sm_s + kSnapOff + h * 512 + lane * 16);
-                    const float4 tg = lds128(sm_s + kTagOff + h * 512 + lane * 16);
-                    const float snv[4] = {sn.x, sn.y, sn.z, sn.w};
-                    const unsigned mk[4] = {__float_as_uint(tg.x), __float_as_uint(tg.y), __float_as_uint(tg.z), __float_as_uint(tg.w)};
-                    unsigned nm[4], nl[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float cm = best[4 * h + q];
-                        const float lo = fminf(cm, snv[q]), hi = fmaxf(cm, snv[q]);
-                        const bool inb = hi <= band_thr(lo, raa[4 * h + q]);
-                        const bool imp = cm < snv[q];
-                        nm[q] = ((imp && !inb) ? 0u : mk[q]) | ((imp || inb) ? bit : 0u);
-                        nl[q] = __float_as_uint(lo);
-                        best[4 * h + q] = kInf;
-                    }
-                    sts128(sm_s + kTagOff + h * 512 + lane * 16, nm[0], nm[1], nm[2], nm[3]);
-                    sts128(sm_s + kSnapOff + h * 512 + lane * 16, nl[0], nl[1], nl[2], nl[3]);
-                }
+            for (int h = 0; h < kR / 4; h++) {
+                const float4 sn = lds128(sm_s + kSnapOff + h * 512 + lane * 16);
+                const float4 tg = lds128(sm_s + kTagOff + h * 512 + lane * 16);
+                const unsigned uch = (unsigned)ch;
+                sts128(sm_s + kTagOff + h * 512 + lane * 16,
+                       best[4 * h] < sn.x ? uch : __float_as_uint(tg.x), best[4 * h + 1] < sn.y ? uch : __float_as_uint(tg.y),
+                       best[4 * h + 2] < sn.z ? uch : __float_as_uint(tg.z), best[4 * h + 3] < sn.w ? uch : __float_as_uint(tg.w));
+                sts128(sm_s + kSnapOff + h * 512 + lane * 16, __float_as_uint(best[4 * h]), __float_as_uint(best[4 * h + 1]),
+                       __float_as_uint(best[4 * h + 2]), __float_as_uint(best[4 * h + 3]));
             }
             if (kcol < p.m) *ck = mykey;
             ck += kChunk; kcol += kChunk;
-            rel++;
             buf ^= kColBuf;
             if (++ch == ch_end) break;
             cp_async_wait_all();
@@ -436,16 +363,13 @@ nn_fwd_kernel(const FwdParams p)
             const int slot = (int)min((long long)wid - own, (long long)ch0);
             u64 *rk0 = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + lane * kR;
             u64 *rk = rk0 + (size_t)slot * kRowsPerBlock;
-            const unsigned hi16 = (ch0tag & 0xffffu) << 16;
 #pragma unroll
             for (int h = 0; h < kR / 4; h++) {
-                const float4 sn = lds128(sm_s + kSnapOff + h * 512 + lane * 16);
                 const float4 tg = lds128(sm_s + kTagOff + h * 512 + lane * 16);
-                // key = span minimum << 32 | first chunk of the span << 16 | mask of candidate chunks (relative, mod 16)
-                rk[4 * h] = ((u64)__float_as_uint(sn.x) << 32) | hi16 | (__float_as_uint(tg.x) & 0xffffu);
-                rk[4 * h + 1] = ((u64)__float_as_uint(sn.y) << 32) | hi16 | (__float_as_uint(tg.y) & 0xffffu);
-                rk[4 * h + 2] = ((u64)__float_as_uint(sn.z) << 32) | hi16 | (__float_as_uint(tg.z) & 0xffffu);
-                rk[4 * h + 3] = ((u64)__float_as_uint(sn.w) << 32) | hi16 | (__float_as_uint(tg.w) & 0xffffu);
+                rk[4 * h] = ((u64)__float_as_uint(best[4 * h]) << 32) | __float_as_uint(tg.x);
+                rk[4 * h + 1] = ((u64)__float_as_uint(best[4 * h + 1]) << 32) | __float_as_uint(tg.y);
+                rk[4 * h + 2] = ((u64)__float_as_uint(best[4 * h + 2]) << 32) | __float_as_uint(tg.z);
+                rk[4 * h + 3] = ((u64)__float_as_uint(best[4 * h + 3]) << 32) | __float_as_uint(tg.w);
             }
             if (ch0 == 0) {
                 // the warp that swept the block's first unit also pads the slots no span reaches
@@ -465,12 +389,11 @@ nn_fwd_kernel(const FwdParams p)
 #endif
 }
 
-// Finalize launch: kFinLanes lanes per output point.  Each group reduces the point's partial keys to the
-// minimum of the sweep's approximate distances, decides which partial results lie within the sweep's error
-// bound of it, and re-evaluates their candidates (32 columns per marked chunk for a point of xyz1, kR rows per
-// marked lane for a point of xyz2) with the reference's arithmetic; the lexicographic minimum of
-// (distance bits, index) is the reference's first argmin.  Almost always exactly one chunk / lane is marked
-// (the fast path: one exposed L2 round trip per point); ties, duplicated points and near-ties take the loop.
+// Finalize launch: kFinLanes lanes per output point.  Each group reduces the point's partial
+// keys, then re-evaluates the tagged candidates (32 columns for a point of xyz1, kR rows for a
+// point of xyz2) with the same arithmetic as the sweep; the lowest index whose distance equals
+// the minimum is the reference's first argmin.  All loads of a phase are independent, so a
+// point costs two dependent L2 round trips.
 #ifndef PNAE_NN_FINLANES
 #define PNAE_NN_FINLANES 4
 #endif
@@ -490,11 +413,12 @@ constexpr int kFinOcc = PNAE_NN_FINOCC;       // resident CTAs per SM the finali
 // FUSED: additionally accumulate loss = sum(g1*dist1) + sum(g2*dist2) and its gradient
 //   d/d a_j = 2 g (a_j - c_nn(j)),   d/d c_nn(j) = -2 g (a_j - c_nn(j))        (tf_nndistance_g.cu:142-148)
 // with g the constant w1 / w2 (pnae_chamfer_loss_grad) or the caller's grad_dist arrays (pnae_nn_distance_fwd_grad),
-// so a Chamfer step needs no separate gradient launch.  dist/idx outputs and the loss value are optional there.
+// so a Chamfer step needs no separate gradient launch and no dist/idx round trip.  dist/idx outputs and the loss
+// value are optional on this path.
 // Grid: y = element, x = CTAs sharing that element's n + m points (its points of xyz1, then those of xyz2) in
 // blocks of kFinThreads/kFinLanes: no divisions anywhere.  The grid is sized to be resident at once; each lane
 // group walks its points with the NEXT point's coordinates and partial keys already in flight while the current
-// point's candidates are fetched and compared.
+// point's candidates are fetched and compared, so a point costs one exposed L2 round trip instead of two.
 struct FinPoint {
     float x, y, z;
     u64 v[4];          // first four partial keys of this lane (slot / row block  sub + t * kFinLanes)
@@ -517,75 +441,15 @@ __device__ __forceinline__ void fin_issue(const FwdParams &p, int e, int pt, int
     for (int t = 0; t < 4; t++) a.v[t] = (sub + t * kFinLanes < count) ? __ldcg(base + t * stride) : ~0ull;
 }
 
-__device__ __forceinline__ u64 dist_key(float d, int idx) { return ((u64)__float_as_uint(d) << 32) | (unsigned)idx; }
-__device__ __forceinline__ float key_val(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
-
-// exact distances of this lane's share (kChunk / kFinLanes columns) of chunk `ch` of xyz2 to the point (x, y, z) of
-// xyz1 -> smallest (distance, index) key
-__device__ __forceinline__ u64 eval_chunk(const float *p2, int m, bool vec2, int ch, int sub, float x, float y, float z)
-{
-    constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
-    const int k0 = ch * kChunk;
-    float cf[kPer * 3];
-    if (kPer % 4 == 0 && vec2 && k0 + kChunk <= m) {
-        const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
-#pragma unroll
-        for (int c = 0; c < kPer * 3 / 4; c++) {
-            const float4 v = __ldg(src + c);
-            cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < kPer; c++) {
-            const int k = min(k0 + sub * kPer + c, m - 1);
-            cf[3 * c] = __ldg(p2 + (size_t)k * 3); cf[3 * c + 1] = __ldg(p2 + (size_t)k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + (size_t)k * 3 + 2);
-        }
-    }
-    u64 acc = ~0ull;
-#pragma unroll
-    for (int c = 0; c < kPer; c++)
-        acc = min(acc, dist_key(pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z), min(k0 + sub * kPer + c, m - 1)));
-    return acc;
-}
-
-// the same for this lane's share (kR / kFinLanes rows) of the kR rows starting at j0 of xyz1, seen from the point
-// (x, y, z) of xyz2
-__device__ __forceinline__ u64 eval_rows(const float *p1, int n, bool vec1, int j0, int sub, float x, float y, float z)
-{
-    constexpr int kPer = kR / kFinLanes;
-    float cf[kPer * 3];
-    if (kPer % 2 == 0 && vec1 && j0 + kR <= n) {
-        const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
-#pragma unroll
-        for (int c = 0; c < kPer * 3 / 2; c++) {
-            const float2 v = __ldg(src + c);
-            cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < kPer; c++) {
-            const int j = min(j0 + sub * kPer + c, n - 1);
-            cf[3 * c] = __ldg(p1 + (size_t)j * 3); cf[3 * c + 1] = __ldg(p1 + (size_t)j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + (size_t)j * 3 + 2);
-        }
-    }
-    u64 acc = ~0ull;
-#pragma unroll
-    for (int c = 0; c < kPer; c++)
-        acc = min(acc, dist_key(pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]), min(j0 + sub * kPer + c, n - 1)));
-    return acc;
-}
-
 template <bool FUSED>
 __global__ void __launch_bounds__(kFinThreads, kFinOcc)
 nn_finalize_kernel(const FwdParams p)
 {
-    // Control flow is warp-uniform wherever lanes talk to each other (full-mask shuffles / ballots; xor offsets 1 and 2
-    // never leave a point's four lanes): points of xyz1 and of xyz2 run through the same code, and the general
-    // path is entered by the whole warp or not at all.
-    constexpr unsigned kFull = 0xffffffffu;
-    static_assert(kFinLanes == 4, "group arithmetic below is written for four lanes per point");
     float loss_acc = 0.f;
-    const int lane = threadIdx.x & 31, sub = lane & (kFinLanes - 1), gbase = lane & ~(kFinLanes - 1);
+    const int sub = threadIdx.x & (kFinLanes - 1);
+    // shuffles stay inside one point's lane group: a warp whose points straddle the xyz1/xyz2 boundary of an
+    // element (n not a multiple of 32/kFinLanes) takes both branches below, so a full-warp mask would be divergent
+    const unsigned gmask = (unsigned)((1ull << kFinLanes) - 1ull) << ((threadIdx.x & 31) & ~(kFinLanes - 1));
     constexpr int kPtsPerCta = kFinThreads / kFinLanes;
     const int per_e = p.n + p.m;
     const int e = blockIdx.y;
@@ -595,9 +459,7 @@ nn_finalize_kernel(const FwdParams p)
     const bool vec2 = (reinterpret_cast<size_t>(p.xyz2) & 15) == 0 && (p.m & 3) == 0;
     const bool vec1 = (reinterpret_cast<size_t>(p.xyz1) & 7) == 0 && (p.n & 1) == 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // launched with programmatic stream serialization
-    asm volatile("griddepcontrol.launch_dependents;");        // the next kernel may queue up behind us the same way
-    float ox, oy, oz;
-    element_centre(p1, p.n, p2, p.m, ox, oy, oz);
+    asm volatile("griddepcontrol.launch_dependents;");        // the gradient kernel may queue up behind us the same way
     int pt = (int)(blockIdx.x * (unsigned)kPtsPerCta + threadIdx.x / kFinLanes);
     const int step = (int)(gridDim.x * (unsigned)kPtsPerCta);
     const int pt_end = (per_e + kPtsPerCta - 1) / kPtsPerCta * kPtsPerCta;      // warp-uniform trip count
@@ -607,113 +469,127 @@ nn_finalize_kernel(const FwdParams p)
         const FinPoint cur = nxt;
         const bool live = pt < per_e;
         const int r = live ? pt : per_e - 1;
-        const bool isrow = r < p.n;               // a point of xyz1 (-> dist1 / idx1) or of xyz2 (-> dist2 / idx2)
-        const int idx = isrow ? r : r - p.n;
         const float x = cur.x, y = cur.y, z = cur.z;
-        const float nrm = infl_norm(__fsub_rn(x, ox), __fsub_rn(y, oy), __fsub_rn(z, oz));    // the sweep's A_j / B_k of this point
-        const int count = isrow ? p.nsl : p.nrb;  // partial results of this point: spans of its row block / row blocks
-        const int rb_own = idx / kRowsPerBlock;
-        const u64 *kbase = isrow ? p.rowkeys + (((size_t)e * p.nrb + rb_own) * p.nslot) * kRowsPerBlock + (idx - rb_own * kRowsPerBlock)
-                                 : p.colkeys + (size_t)e * p.nrb * p.m + idx;
-        const size_t kstride = isrow ? kRowsPerBlock : p.m;       // between consecutive partial results
-
-        // ---- the smallest approximate minimum over all partial results (padding keys are all-ones)
-        unsigned h = min(min((unsigned)(cur.v[0] >> 32), (unsigned)(cur.v[1] >> 32)), min((unsigned)(cur.v[2] >> 32), (unsigned)(cur.v[3] >> 32)));
-        if (count > 4 * kFinLanes)
-            for (int t = sub + 4 * kFinLanes; t < count; t += kFinLanes) h = min(h, (unsigned)(__ldcg(kbase + (size_t)t * kstride) >> 32));
-        __syncwarp();
-        h = min(h, __shfl_xor_sync(kFull, h, 1));
-        h = min(h, __shfl_xor_sync(kFull, h, 2));
-        const float thr = band_thr(__uint_as_float(h), nrm);
-
-        // ---- which of this lane's partial results lie within the bound of it
-        int cnt = 0, mt = 0;
-        unsigned lo = 0;
+        if (r < p.n) {
+            // point j of xyz1 -> dist1 / idx1
+            const int j = r;
+            u64 key = min(min(cur.v[0], cur.v[1]), min(cur.v[2], cur.v[3]));   // (min bits, chunk): lower distance, then lower chunk
+            if (p.nsl > 4 * kFinLanes) {
+                const int rb = j / kRowsPerBlock;
+                const u64 *rk = p.rowkeys + (((size_t)e * p.nrb + rb) * p.nslot) * kRowsPerBlock + (j - rb * kRowsPerBlock);
+                for (int sl = sub + 4 * kFinLanes; sl < p.nsl; sl += kFinLanes) key = min(key, __ldcg(rk + (size_t)sl * kRowsPerBlock));
+            }
 #pragma unroll
-        for (int t = 3; t >= 0; t--) {
-            const bool inb = key_val(cur.v[t]) <= thr;            // NaN (padding) compares false
-            if (inb) { lo = (unsigned)cur.v[t]; mt = t; }
-            cnt += inb;
-        }
-        if (count > 4 * kFinLanes)
-            for (int t = sub + 4 * kFinLanes; t < count; t += kFinLanes) cnt += 2 * (key_val(__ldcg(kbase + (size_t)t * kstride)) <= thr);
-        // one candidate set only: a point of xyz1 wants one chunk (one mask bit, no aliased chunk inside the span),
-        // a point of xyz2 one lane of one row block
-        const unsigned bitsel = isrow ? (lo & 0xffffu) : lo;
-        const int first = __ffs(bitsel) - 1;
-        const int c0 = (int)((lo >> 16) << p.tsh);
-        const int chf = c0 + first;
-        bool single = cnt == 1 && bitsel != 0 && (bitsel & (bitsel - 1)) == 0;
-        if (isrow) single = single && chf + 16 >= min(p.nch, c0 + p.maxspan + (1 << p.tsh) - 1);
-        __syncwarp();
-        const unsigned g1 = (__ballot_sync(kFull, cnt >= 1) >> gbase) & 0xfu;
-        const unsigned g2 = (__ballot_sync(kFull, cnt >= 1 && !single) >> gbase) & 0xfu;
-        const bool simple = g1 != 0 && (g1 & (g1 - 1)) == 0 && g2 == 0;
-        // first candidate of the simple case, from the lane that owns it
-        int cbase = isrow ? chf : (sub + mt * kFinLanes) * kRowsPerBlock + first * kR;
-        cbase = __shfl_sync(kFull, cbase, gbase + (g1 ? __ffs(g1) - 1 : 0));
-        if (pt + step < pt_end) fin_issue(p, e, pt + step, sub, nxt);           // in flight while the candidates arrive
-
-        u64 acc = ~0ull;        // this lane's smallest exact (distance, index) key
-        if (simple) {
-            // the group shares the 32 columns of one chunk / the kR rows of one lane
-            acc = isrow ? eval_chunk(p2, p.m, vec2, cbase, sub, x, y, z) : eval_rows(p1, p.n, vec1, cbase, sub, x, y, z);
-        }
-        __syncwarp();
-        if (__any_sync(kFull, !simple)) {
-            if (!simple) {
-                // general case (near-ties, duplicated points, exact ties): every lane takes all marked candidates of
-                // its own partial results by itself
-                for (int t = sub; t < count; t += kFinLanes) {
-                    const u64 k = __ldcg(kbase + (size_t)t * kstride);
-                    if (!(key_val(k) <= thr)) continue;
-                    if (isrow) {
-                        unsigned mk = (unsigned)k & 0xffffu;
-                        const int s0 = (int)(((unsigned)k >> 16) << p.tsh);
-                        const int send = min(p.nch, s0 + p.maxspan + (1 << p.tsh) - 1);
-                        while (mk) {
-                            const int beta = __ffs(mk) - 1;
-                            mk &= mk - 1;
-                            for (int ch = s0 + beta; ch < send; ch += 16)
-#pragma unroll 1
-                                for (int q = 0; q < kFinLanes; q++) acc = min(acc, eval_chunk(p2, p.m, vec2, ch, q, x, y, z));
-                        }
-                    } else {
-                        unsigned wl = (unsigned)k;
-                        while (wl) {
-                            const int l = __ffs(wl) - 1;
-                            wl &= wl - 1;
-#pragma unroll 1
-                            for (int q = 0; q < kFinLanes; q++) acc = min(acc, eval_rows(p1, p.n, vec1, t * kRowsPerBlock + l * kR, q, x, y, z));
-                        }
-                    }
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) key = min(key, (u64)__shfl_xor_sync(gmask, key, o));
+            const float want = __uint_as_float((unsigned)(key >> 32));
+            const int k0 = (int)(unsigned)key * kChunk;
+            constexpr int kPer = kChunk / kFinLanes;          // candidates per lane, contiguous
+            float cf[kPer * 3];
+            if (kPer % 4 == 0 && vec2 && k0 + kChunk <= p.m) {
+                const float4 *src = reinterpret_cast<const float4 *>(p2 + (size_t)(k0 + sub * kPer) * 3);
+#pragma unroll
+                for (int c = 0; c < kPer * 3 / 4; c++) {
+                    const float4 v = __ldg(src + c);
+                    cf[4 * c] = v.x; cf[4 * c + 1] = v.y; cf[4 * c + 2] = v.z; cf[4 * c + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kPer; c++) {
+                    const int k = min(k0 + sub * kPer + c, p.m - 1);
+                    cf[3 * c] = __ldg(p2 + k * 3); cf[3 * c + 1] = __ldg(p2 + k * 3 + 1); cf[3 * c + 2] = __ldg(p2 + k * 3 + 2);
                 }
             }
-            __syncwarp();
-        }
-        acc = min(acc, (u64)__shfl_xor_sync(kFull, acc, 1));
-        acc = min(acc, (u64)__shfl_xor_sync(kFull, acc, 2));
-        if (live && sub == 0) {
-            const float want = key_val(acc);
-            const int nn = min((int)(unsigned)acc & 0x7fffffff, (isrow ? p.m : p.n) - 1);     // (the clamp only matters for NaN inputs)
-            float *dist = isrow ? p.dist1 : p.dist2;
-            const size_t o = isrow ? (size_t)e * p.n + idx : (size_t)e * p.m + idx;
-            if (dist != nullptr) {
-                dist[o] = want;
-                (isrow ? p.idx1 : p.idx2)[o] = nn;
+            if (pt + step < pt_end) fin_issue(p, e, pt + step, sub, nxt);   // in flight while the candidates arrive
+            int found = 0x7fffffff;
+#pragma unroll
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(cf[3 * c] - x, cf[3 * c + 1] - y, cf[3 * c + 2] - z) == want) found = min(k0 + sub * kPer + c, p.m - 1);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+            if (live && sub == 0) {
+                const int nn = found == 0x7fffffff ? min(k0, p.m - 1) : found;
+                if (p.dist1 != nullptr) {
+                    p.dist1[(size_t)e * p.n + j] = want;
+                    p.idx1[(size_t)e * p.n + j] = nn;
+                }
+                if (FUSED) {
+                    const float w = p.gd1 != nullptr ? __ldg(p.gd1 + (size_t)e * p.n + j) : p.w1;
+                    loss_acc = fmaf(w, want, loss_acc);
+                    const float g = __fmul_rn(w, 2.0f);
+                    float *ga = p.gxyz1 + ((size_t)e * p.n + j) * 3, *gc = p.gxyz2 + ((size_t)e * p.m + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p2 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p2 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p2 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
-            if (FUSED) {
-                const float *gd = isrow ? p.gd1 : p.gd2;
-                const float w = gd != nullptr ? __ldg(gd + o) : (isrow ? p.w1 : p.w2);
-                loss_acc = fmaf(w, want, loss_acc);
-                const float g = __fmul_rn(w, 2.0f);
-                const float *oc = (isrow ? p2 : p1) + (size_t)nn * 3;                   // the nearest neighbour's coordinates
-                float *ga = (isrow ? p.gxyz1 : p.gxyz2) + o * 3;
-                float *gc = isrow ? p.gxyz2 + ((size_t)e * p.m + nn) * 3 : p.gxyz1 + ((size_t)e * p.n + nn) * 3;
-                const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(oc))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(oc + 1)));
-                const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(oc + 2)));
-                atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
-                atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+        } else {
+            // point k of xyz2 -> dist2 / idx2
+            const int k = r - p.n;
+            u64 key = ~0ull;       // (min bits, row block): the lowest row block wins ties
+            unsigned who = 1;      // ballot of the lanes that held the minimum in that row block
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int rb = sub + t * kFinLanes;
+                const u64 cand = (cur.v[t] & 0xffffffff00000000ull) | (unsigned)rb;
+                if (rb < p.nrb && cand < key) { key = cand; who = (unsigned)cur.v[t]; }
+            }
+            if (p.nrb > 4 * kFinLanes) {
+                const u64 *ck = p.colkeys + (size_t)e * p.nrb * p.m + k;
+                for (int rb = sub + 4 * kFinLanes; rb < p.nrb; rb += kFinLanes) {
+                    const u64 v = __ldcg(ck + (size_t)rb * p.m);
+                    const u64 cand = (v & 0xffffffff00000000ull) | (unsigned)rb;
+                    if (cand < key) { key = cand; who = (unsigned)v; }
+                }
+            }
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) {
+                const u64 k2 = __shfl_xor_sync(gmask, key, o);
+                const unsigned w2 = __shfl_xor_sync(gmask, who, o);
+                if (k2 < key) { key = k2; who = w2; }
+            }
+            const int rbw = (int)(unsigned)key;
+            const float want = __uint_as_float((unsigned)(key >> 32));
+            const int j0 = rbw * kRowsPerBlock + (__ffs(who) - 1) * kR;     // lowest lane holding the min
+            constexpr int kPer = kR / kFinLanes;
+            float cf[kPer * 3];
+            if (kPer % 2 == 0 && vec1 && j0 + kR <= p.n) {
+                const float2 *src = reinterpret_cast<const float2 *>(p1 + (size_t)(j0 + sub * kPer) * 3);
+#pragma unroll
+                for (int c = 0; c < kPer * 3 / 2; c++) {
+                    const float2 v = __ldg(src + c);
+                    cf[2 * c] = v.x; cf[2 * c + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kPer; c++) {
+                    const int j = min(j0 + sub * kPer + c, p.n - 1);
+                    cf[3 * c] = __ldg(p1 + j * 3); cf[3 * c + 1] = __ldg(p1 + j * 3 + 1); cf[3 * c + 2] = __ldg(p1 + j * 3 + 2);
+                }
+            }
+            if (pt + step < pt_end) fin_issue(p, e, pt + step, sub, nxt);   // in flight while the candidates arrive
+            int found = 0x7fffffff;
+#pragma unroll
+            for (int c = kPer - 1; c >= 0; c--)
+                if (pnae_sqdist(x - cf[3 * c], y - cf[3 * c + 1], z - cf[3 * c + 2]) == want) found = min(j0 + sub * kPer + c, p.n - 1);
+#pragma unroll
+            for (int o = kFinLanes / 2; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(gmask, found, o));
+            if (live && sub == 0) {
+                const int nn = found == 0x7fffffff ? min(j0, p.n - 1) : found;
+                if (p.dist2 != nullptr) {
+                    p.dist2[(size_t)e * p.m + k] = want;
+                    p.idx2[(size_t)e * p.m + k] = nn;
+                }
+                if (FUSED) {
+                    const float w = p.gd2 != nullptr ? __ldg(p.gd2 + (size_t)e * p.m + k) : p.w2;
+                    loss_acc = fmaf(w, want, loss_acc);
+                    const float g = __fmul_rn(w, 2.0f);
+                    float *ga = p.gxyz2 + ((size_t)e * p.m + k) * 3, *gc = p.gxyz1 + ((size_t)e * p.n + nn) * 3;
+                    const float vx = __fmul_rn(g, __fsub_rn(x, __ldg(p1 + nn * 3))), vy = __fmul_rn(g, __fsub_rn(y, __ldg(p1 + nn * 3 + 1)));
+                    const float vz = __fmul_rn(g, __fsub_rn(z, __ldg(p1 + nn * 3 + 2)));
+                    atomicAdd(ga, vx); atomicAdd(ga + 1, vy); atomicAdd(ga + 2, vz);
+                    atomicAdd(gc, -vx); atomicAdd(gc + 1, -vy); atomicAdd(gc + 2, -vz);
+                }
             }
         }
     }
@@ -898,9 +774,6 @@ int launch_fwd(const char *op, int b, int n, const float *xyz1, int m, const flo
         p.w1 = w1; p.w2 = w2; p.zero_loss = (e0 == 0 && loss != nullptr);
         p.gd1 = gd1 ? gd1 + (size_t)e0 * n : nullptr;
         p.gd2 = gd2 ? gd2 + (size_t)e0 * m : nullptr;
-        p.maxspan = (int)min((long long)pl.nch, (p.units + p.warps - 1) / p.warps);
-        p.tsh = 0;
-        while ((((long long)pl.nch - 1) >> p.tsh) + 1 > 65535) p.tsh++;
         // 32-bit index arithmetic whenever the point count and the span formula's (u+1)*warps fit
         const bool force64 = getenv("PNAE_NN_INDEX64") != nullptr;            // test hook for the wide path, read on every call
         const long long groups = (long long)p.be * ((long long)n + m);

@@ -15,6 +15,13 @@
 namespace {
 
 constexpr int kL = PNAE_NUM_LEVELS;
+// OFF: measured on B200 it saves 7 % (approx_match) / 13 % (match_cost), but the SFU's 2^-22 relative error becomes
+// 2^-20 on the derived exponentials and the ill-conditioned schedule amplifies that past the parity bar (match_cost
+// up to 3.4e-5 relative against the oracle, gradients 3x farther from the fp64 truth than the reference kernels).
+#ifndef PNAE_EMD_POW4
+#define PNAE_EMD_POW4 0
+#endif
+constexpr bool kPow4 = PNAE_EMD_POW4 != 0;   // E_j = E_{j+1}^4 for every other level (two FMULs instead of a MUFU.EX2)
 
 // ---------------------------------------------------------------------------
 // factor path
@@ -105,13 +112,22 @@ match_cost_factors_kernel(int n, int m, const float *__restrict__ xyz1, const fl
             const float2 dz = __fadd2_rn(z1, mk2(-zr0.x, -zr0.y));
             const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
             float2 mv = mk2(0, 0);
+            float2 ev[kL - 1];
 #pragma unroll
-            for (int j = 0; j < kL - 1; j++) {
-                const float cj = pnae_level_scale(j);
-                const float2 u = __fmul2_rn(d, mk2(cj, cj));
-                const float2 e = mk2(pnae_ex2(u.x), pnae_ex2(u.y));
-                mv = __ffma2_rn(__fmul2_rn(e, rl[j]), rr[j], mv);
+            for (int j = kL - 2; j >= 0; j--) {
+                if (kPow4 && (j & 1)) {
+                    // level_j = 4 level_{j+1}: E_j = E_{j+1}^4, two multiplies on the FMA pipe instead of a MUFU.EX2
+                    // (every other level only, so the SFU's 2^-22 relative error grows to 2^-20 and no further)
+                    const float2 e2 = __fmul2_rn(ev[j + 1], ev[j + 1]);
+                    ev[j] = __fmul2_rn(e2, e2);
+                } else {
+                    const float cj = pnae_level_scale(j);
+                    const float2 u = __fmul2_rn(d, mk2(cj, cj));
+                    ev[j] = mk2(pnae_ex2(u.x), pnae_ex2(u.y));
+                }
             }
+#pragma unroll
+            for (int j = 0; j < kL - 1; j++) mv = __ffma2_rn(__fmul2_rn(ev[j], rl[j]), rr[j], mv);   // level order, like `match+=w`
             mv = __ffma2_rn(rl[kL - 1], rr[kL - 1], mv);                  // last level: E == 1
             const float2 rs = mk2(pnae_rsqrt(fmaxf(d.x, 1e-20f)), pnae_rsqrt(fmaxf(d.y, 1e-20f)));   // :243, :281
             csum = __ffma2_rn(__fmul2_rn(d, rs), mv, csum);               // sqrt(d) * match   (:207-208)

@@ -213,6 +213,43 @@ PNAE_API int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf
                                     float *out_max, float *out_min, float *out_sum, float *out_sumsq,
                                     const float *sign, int *out_arg, void *stream);
 
+/* ---- PointNet encoder: layers 1-4 (3 -> 64 -> 64 -> 64 -> 128), one kernel per layer ---------- */
+
+/* Replace, for the first four layers of get_model (models/model.py:40-56), the per-layer TF graph segment
+ * conv2d -> bias -> BatchNorm -> ReLU (utils/tf_util.py:155-185, 514-533).  A layer kernel reads the previous layer's
+ * RAW output (before BatchNorm), applies that layer's folded BatchNorm + ReLU  a = relu(s*y + t)  on the way in,
+ * multiplies by its weight on the tensor cores (3xTF32: fp32 accuracy), adds the bias, writes its own raw output and
+ * returns the per-channel sum and sum of squares of it: stats (2, kout) = { sum_p y[p,c], sum_p y[p,c]^2 }, from which
+ * the caller forms the batch statistics of training-mode BatchNorm (or ignores them in inference mode).  For
+ * pnae_mlp_layer the stats buffer must have room for 2*kout + kout/64 floats: the trailing words are the kernel's tile
+ * counters.
+ * npts = batch * points; all matrices row-major fp32; w is (kin, kout) like the reference's [1,1,kin,kout] kernel. */
+PNAE_API int pnae_mlp_first(long long npts, const float *xyz, const float *w /* (3,64) */, const float *bias,
+                            float *out /* (npts,64) */, float *stats /* (2,64) */, void *stream);
+/* The previous layer's BatchNorm is given by its raw statistics (stats_prev (2,kin), training != 0: batch statistics, and
+ * the kernel also performs TF's moving-average update of moving_mean_prev / moving_var_prev with the biased variance,
+ * utils/tf_util.py:529-533) or by its moving statistics (training == 0; stats_prev may be NULL). */
+PNAE_API int pnae_mlp_layer(long long npts, int kin /* 64 */, int kout /* 64 or 128 */, const float *in,
+                            const float *stats_prev, const float *gamma_prev, const float *beta_prev,
+                            float *moving_mean_prev, float *moving_var_prev, float eps, float decay, int training,
+                            const float *w, const float *bias, float *out, float *stats, void *stream);
+/* BatchNorm bookkeeping of one layer on its own (the layer kernels do this in their prologue; this entry exists for callers
+ * that want the folded scale s = gamma/sqrt(var+eps) and shift t = beta - mean*s themselves). */
+PNAE_API int pnae_bn_fold(int k, const float *stats, double count, const float *gamma, const float *beta, float eps, float decay,
+                          int training, float *moving_mean, float *moving_var, float *s_out, float *t_out, void *stream);
+/* relu(BatchNorm(y)) of the last of these layers (BatchNorm given like in pnae_mlp_layer) as the bf16 (npts, k) operand of
+ * pnae_encoder_conv_pool. */
+PNAE_API int pnae_mlp_apply_bf16(long long npts, int k, const float *in, const float *stats, const float *gamma, const float *beta,
+                                 float *moving_mean, float *moving_var, float eps, float decay, int training,
+                                 void *out_bf16, void *stream);
+/* conv5's bias + BatchNorm + ReLU + max-pool finish on (b, c), one launch: from pnae_encoder_conv_pool's max / min / sum /
+ * sumsq to pooled (b,c) = relu((ext0 - mean0) * gamma * inv + beta), ext0 = max where gamma >= 0 else min; count = b * n.
+ * Also returns what the backward needs: inv (c), mean0 (c) (of x @ w without the bias), ext0 (b,c), z (b,c). */
+PNAE_API int pnae_conv5_finish(int b, int c, double count, const float *vmax, const float *vmin, const float *vsum, const float *vsq,
+                               const float *bias, const float *gamma, const float *beta, float *moving_mean, float *moving_var,
+                               float eps, float decay, int training, float *pooled, float *inv, float *mean0, float *ext0, float *z,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,435 @@
+// shared_mlp.cu -- layers 1-4 of the PointNet encoder (3 -> 64 -> 64 -> 64 -> 128) for sm_100a.
+//
+// Reference path: get_model, models/model.py:40-56 -- four tf_util.conv2d calls with [1,3] / [1,1] kernels, i.e.
+// per-point linear maps, each followed by bias, BatchNorm (training mode: statistics over all B*N points) and
+// ReLU (utils/tf_util.py:155-185, 514-533).  The reference graph runs every one of these as its own op and
+// writes / re-reads the (B*N, C) activation between them; round 1 of this repository did the same through
+// cuBLAS + library batch-norm kernels.
+//
+// Training-mode BatchNorm needs a layer's statistics over ALL points before the next layer may start, so the chain
+// is one kernel per layer, each of which
+//   * reads the previous layer's RAW output y (fp32) once (cp.async, double-buffered tiles) and applies that layer's
+//     folded BatchNorm + ReLU when a fragment is read (a = relu(s*y + t); s, t per channel), so normalised
+//     activations never exist in HBM;
+//   * multiplies by W on the tensor cores (mma.sync m16n8k8 TF32 with the 3xTF32 split a = hi + lo, so the
+//     product keeps fp32 accuracy: the reference computes these layers in fp32) and adds the bias;
+//   * writes its own raw output once and accumulates the per-channel sum and sum of squares BatchNorm needs in
+//     the epilogue (registers -> shuffles -> shared -> one atomic per channel per CTA).
+// The layers are memory-bound (K <= 64: 16.8 MB in, 16.8 / 33.5 MB out at B*N = 65536), which is why these are
+// plain warp-level MMAs and not a tcgen05 pipeline: the tensor pipe is idle either way.  The last kernel applies
+// layer 4's BatchNorm + ReLU and emits the bf16 K-major operand of the conv5 tcgen05 kernel (encoder.cu) directly.
+#include <cuda_bf16.h>
+
+#include "pnae_common.cuh"
+
+namespace {
+
+constexpr int kMlpThreads = 128;     // 4 warps, 16 points (one MMA row tile) each
+constexpr int kTileP = 64;           // points per CTA tile: 1024 tiles at B*N = 65536 balance 148 SMs to 1 %
+constexpr int kCols = 64;            // output channels per CTA (grid.y walks wider layers)
+constexpr int kKin = 64;             // input channels of layers 2-4
+constexpr int kLdA = kKin + 4;       // padded leading dimensions: conflict-free fragment loads (see below)
+constexpr int kLdW = kCols;           // W is kept in fragment order (see the kernel): no padding needed
+
+// 3xTF32 split by TRUNCATION: hi = the top 19 bits (what the tensor core reads of an fp32 register anyway), lo = v - hi
+// (exact).  One LOP3 + one FADD per element; cvt.rna.tf32 expands to ~5 instructions on sm_100 and the 2^-21
+// relative difference is below the dropped lo*lo term.
+__device__ __forceinline__ unsigned tf32_hi(float v) { return __float_as_uint(v) & 0xffffe000u; }
+__device__ __forceinline__ unsigned tf32_lo(float v, unsigned hi) { return __float_as_uint(v - __uint_as_float(hi)); }
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// The previous layer's BatchNorm as the consumer kernels see it: batch statistics from that layer's sums (training) or
+// its moving statistics (inference), folded to scale s = gamma / sqrt(var + eps) and shift t = beta - mean * s.  Every
+// CTA computes the same values from the same inputs; CTA (0,0) also performs TF's moving-average update
+// (moving = decay * moving + (1 - decay) * batch, biased variance: tf.contrib.layers.batch_norm, tf_util.py:529-533).
+struct BnPrev {
+    const float *stats;          // (2, k) sum / sum of squares of the layer's raw output, or NULL in inference mode
+    const float *gamma, *beta;
+    float *moving_mean, *moving_var;
+    float inv_count, eps, decay;
+    int training;
+};
+
+__device__ __forceinline__ void bn_fold_channel(const BnPrev &bn, int k, int c, bool update, float &s, float &t)
+{
+    float mean, var;
+    if (bn.training) {
+        mean = bn.stats[c] * bn.inv_count;
+        var = fmaxf(fmaf(-mean, mean, bn.stats[k + c] * bn.inv_count), 0.f);
+        if (update) {
+            bn.moving_mean[c] = fmaf(bn.decay, bn.moving_mean[c], (1.f - bn.decay) * mean);
+            bn.moving_var[c] = fmaf(bn.decay, bn.moving_var[c], (1.f - bn.decay) * var);
+        }
+    } else {
+        mean = bn.moving_mean[c]; var = bn.moving_var[c];
+    }
+    s = bn.gamma[c] / sqrtf(var + bn.eps);
+    t = fmaf(-mean, s, bn.beta[c]);
+}
+
+// Layer 1: y[p, c] = xyz[p, :] . W[:, c] + bias[c]   (K = 3: three FMAs per output, write-bound)
+// 16 threads per point (4 channels each, float4 stores); a thread's channel group is fixed, so its statistics stay
+// in registers for the whole grid-stride loop.
+__global__ void __launch_bounds__(256)
+mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__restrict__ w, const float *__restrict__ bias,
+                 float *__restrict__ out, float *__restrict__ stats)
+{
+    __shared__ float s_stats[2][64];
+    if (threadIdx.x < 128) s_stats[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
+    __syncthreads();
+    const int cg = threadIdx.x & 15;           // channels 4*cg .. 4*cg+3
+    float wx[4], wy[4], wz[4], bb[4], sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        wx[j] = __ldg(w + 4 * cg + j); wy[j] = __ldg(w + 64 + 4 * cg + j); wz[j] = __ldg(w + 128 + 4 * cg + j);
+        bb[j] = __ldg(bias + 4 * cg + j);
+    }
+    for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < npts; p += (long long)gridDim.x * 16) {
+        const float x = __ldg(xyz + p * 3), y = __ldg(xyz + p * 3 + 1), z = __ldg(xyz + p * 3 + 2);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = fmaf(z, wz[j], fmaf(y, wy[j], fmaf(x, wx[j], bb[j])));
+            sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]);
+        }
+        *reinterpret_cast<float4 *>(out + p * 64 + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        // the 16 threads of a half-warp with the same cg differ in bit 4 of the lane only
+        sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], 16); sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
+        if ((threadIdx.x & 16) == 0) { atomicAdd(&s_stats[0][4 * cg + j], sum[j]); atomicAdd(&s_stats[1][4 * cg + j], sq[j]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) atomicAdd(stats + threadIdx.x, s_stats[threadIdx.x >> 6][threadIdx.x & 63]);
+}
+
+// Layers 2-4: out[p, c0 + c] = relu(s_prev * in[p, :] + t_prev) . W[:, c0 + c] + bias[c0 + c],  c < 64, c0 = 64 * blockIdx.y
+// Persistent CTAs over 128-point tiles.  Fragment layouts of mma.m16n8k8 (g = lane / 4, t = lane % 4):
+//   A (16x8, row): a0 = (g, t)  a1 = (g+8, t)  a2 = (g, t+4)  a3 = (g+8, t+4)
+//   B (8x8, col):  b0 = (k=t, n=g)  b1 = (k=t+4, n=g)
+//   C (16x8):      c0 = (g, 2t)  c1 = (g, 2t+1)  c2 = (g+8, 2t)  c3 = (g+8, 2t+1)
+// With rows of A padded to 68 floats the 32 lanes of an A fragment load hit 32 distinct banks; W is stored in fragment order.
+__global__ void __launch_bounds__(kMlpThreads)
+mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const BnPrev bn, const float *__restrict__ w,
+                 const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *As = reinterpret_cast<float *>(smem_raw);                 // [2][kTileP][kLdA]   raw input tiles (double buffer)
+    unsigned *Whi = reinterpret_cast<unsigned *>(As + 2 * kTileP * kLdA); // [kKin][kLdW]     tf32(W)
+    unsigned *Wlo = Whi + kKin * kLdW;                                // [kKin][kLdW]     tf32(W - hi)
+    float *sp = reinterpret_cast<float *>(Wlo + kKin * kLdW);         // [kKin] s_prev, [kKin] t_prev
+    float *tp = sp + kKin;
+    float *s_stats = tp + kKin;                                       // [2][kCols]
+    const int c0 = blockIdx.y * kCols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+    // W in FRAGMENT ORDER: for k-step ks and n-tile pair np, the four values lane (g, t) needs -- (b0, b1) of n-tile 2 np
+    // and (b0, b1) of n-tile 2 np + 1, b0 = W[8 ks + t][8 nt + g], b1 = W[8 ks + t + 4][8 nt + g] -- are 16 contiguous
+    // bytes at [((ks*4 + np)*32 + lane)*4]: four conflict-free LDS.128 per k-step land every B fragment in the
+    // adjacent register pair the MMA wants (no register moves)
+#pragma unroll 8
+    for (int i = threadIdx.x; i < kKin * kCols; i += kMlpThreads) {
+        const int k = i / kCols, c = i - k * kCols;
+        const float v = __ldg(w + (size_t)k * kout + c0 + c);
+        const unsigned hi = tf32_hi(v);
+        const int ks = k >> 3, kh = (k >> 2) & 1, tt = k & 3, nt = c >> 3, gg = c & 7;
+        // [ks][n-tile pair np = nt / 2][lane][nt & 1][kh]: one LDS.128 = the (b0, b1) register pairs of two n-tiles
+        const int idx = (((ks * 4 + (nt >> 1)) * 32 + gg * 4 + tt) << 2) + ((nt & 1) << 1) + kh;
+        Whi[idx] = hi;
+        Wlo[idx] = tf32_lo(v, hi);
+    }
+    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0 && blockIdx.y == 0, sp[threadIdx.x], tp[threadIdx.x]);
+    if (threadIdx.x < 2 * kCols) s_stats[threadIdx.x] = 0.f;
+    float bcol[8][2], sum[8][2], sq[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { bcol[nt][j] = __ldg(bias + c0 + nt * 8 + 2 * t + j); sum[nt][j] = 0.f; sq[nt][j] = 0.f; }
+    __syncthreads();
+
+    // Input tiles are double-buffered: the NEXT tile's raw rows arrive by cp.async while this one is multiplied, and the
+    // previous layer's BatchNorm + ReLU is applied when a fragment is read (rows past the end repeat the last row; the
+    // epilogue ignores them).
+    const long long ntiles = (npts + kTileP - 1) / kTileP;
+    // a thread always copies the same 16-byte column slot (q) of rows r0, r0 + 8, ...: one pointer, constant strides
+    const int q = threadIdx.x & 15, r0 = threadIdx.x >> 4;
+    const unsigned as_s = (unsigned)__cvta_generic_to_shared(As) + (unsigned)((r0 * kLdA + 4 * q) * sizeof(float));
+    auto issue = [&](long long tile, int buf) {
+        const long long p0 = tile * kTileP + r0;
+        const unsigned d = as_s + (unsigned)(buf * kTileP * kLdA * sizeof(float));
+#pragma unroll
+        for (int j = 0; j < kTileP / 8; j++) {
+            const long long row = min(p0 + 8 * j, npts - 1);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (unsigned)(8 * j * kLdA * sizeof(float))), "l"(in + row * kKin + 4 * q));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // tiles are handed out dynamically (one atomic per tile on the counter word behind the statistics): with 1024
+    // tiles on 148 SMs a static split leaves a third of the CTAs one tile short and their SMs idle at the end
+    unsigned *counter = reinterpret_cast<unsigned *>(stats + 2 * (size_t)kout) + blockIdx.y;
+    __shared__ long long s_next;
+    auto fetch = [&]() -> long long {
+        if (threadIdx.x == 0) s_next = (long long)atomicAdd(counter, 1u);
+        __syncthreads();
+        const long long v = s_next;
+        __syncthreads();
+        return v;
+    };
+    int buf = 0;
+    long long tile = fetch();
+    if (tile < ntiles) issue(tile, 0);
+    for (; tile < ntiles; buf ^= 1) {
+        const long long p0 = tile * kTileP;
+        const long long nxt = fetch();
+        if (nxt < ntiles) {
+            issue(nxt, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+
+        // ---- 16 points x 64 channels per warp, K = 64 in 8 steps; 3xTF32: hi*hi + lo*hi + hi*lo
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[nt][j] = 0.f;
+        const float *Aw = As + (size_t)buf * kTileP * kLdA + (warp * 16) * kLdA;
+#pragma unroll
+        for (int ks = 0; ks < kKin / 8; ks++) {
+            const float s0 = sp[ks * 8 + t], t0 = tp[ks * 8 + t], s1 = sp[ks * 8 + t + 4], t1 = tp[ks * 8 + t + 4];
+            unsigned ahi[4], alo[4];
+            {
+                const float *ap = Aw + g * kLdA + ks * 8 + t;
+                const float a[4] = {fmaxf(fmaf(ap[0], s0, t0), 0.f), fmaxf(fmaf(ap[8 * kLdA], s0, t0), 0.f),
+                                    fmaxf(fmaf(ap[4], s1, t1), 0.f), fmaxf(fmaf(ap[8 * kLdA + 4], s1, t1), 0.f)};
+#pragma unroll
+                for (int j = 0; j < 4; j++) { ahi[j] = tf32_hi(a[j]); alo[j] = tf32_lo(a[j], ahi[j]); }
+            }
+            unsigned bhi[8][2], blo[8][2];
+#pragma unroll
+            for (int np = 0; np < 4; np++) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(Whi + (((ks * 4 + np) * 32 + lane) << 2));
+                const uint4 l = *reinterpret_cast<const uint4 *>(Wlo + (((ks * 4 + np) * 32 + lane) << 2));
+                bhi[2 * np][0] = h.x; bhi[2 * np][1] = h.y; bhi[2 * np + 1][0] = h.z; bhi[2 * np + 1][1] = h.w;
+                blo[2 * np][0] = l.x; blo[2 * np][1] = l.y; blo[2 * np + 1][0] = l.z; blo[2 * np + 1][1] = l.w;
+            }
+            // three passes over the 8 accumulators (small terms first): consecutive MMAs are independent, and the
+            // three that feed one accumulator are 8 instructions apart instead of back to back
+#ifndef PNAE_MLP_TF32X1           // (tuning experiment: single-pass TF32, 1e-3 accuracy)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], alo, bhi[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], ahi, blo[nt]);
+#endif
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], ahi, bhi[nt]);
+        }
+        __syncthreads();          // every warp is done with this buffer: the next iteration refills it
+
+        // ---- epilogue: bias, raw output, statistics over the live rows
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+                const long long p = p0 + warp * 16 + g + 8 * h;
+                if (p < npts) {
+                    float *op = out + p * kout + c0 + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const float v0 = acc[nt][2 * h] + bcol[nt][0], v1 = acc[nt][2 * h + 1] + bcol[nt][1];
+                        *reinterpret_cast<float2 *>(op + nt * 8) = make_float2(v0, v1);
+                        sum[nt][0] += v0; sum[nt][1] += v1;
+                        sq[nt][0] = fmaf(v0, v0, sq[nt][0]); sq[nt][1] = fmaf(v1, v1, sq[nt][1]);
+                    }
+                }
+            }
+        tile = nxt;
+    }
+    // lanes with the same t hold the same channels: fold the 8 values of g
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            float a = sum[nt][j], b = sq[nt][j];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (g == 0) { atomicAdd(&s_stats[nt * 8 + 2 * t + j], a); atomicAdd(&s_stats[kCols + nt * 8 + 2 * t + j], b); }
+        }
+    __syncthreads();
+    if (threadIdx.x < 2 * kCols) {
+        const int which = threadIdx.x / kCols, c = threadIdx.x - which * kCols;
+        atomicAdd(stats + (size_t)which * kout + c0 + c, s_stats[threadIdx.x]);
+    }
+}
+
+// relu(s * y + t) -> bf16, (npts, k) row-major = the K-major operand tile layout the conv5 kernel's TMA map expects
+__global__ void __launch_bounds__(256)
+mlp_apply_bf16_kernel(long long n4, int k, const float *__restrict__ in, const BnPrev bn, __nv_bfloat16 *__restrict__ out)
+{
+    __shared__ float s[256], t[256];
+    for (int c = threadIdx.x; c < k; c += blockDim.x) bn_fold_channel(bn, k, c, blockIdx.x == 0, s[c], t[c]);
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % k);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(in) + i);
+        const float a0 = fmaxf(fmaf(v.x, s[c], t[c]), 0.f), a1 = fmaxf(fmaf(v.y, s[c + 1], t[c + 1]), 0.f);
+        const float a2 = fmaxf(fmaf(v.z, s[c + 2], t[c + 2]), 0.f), a3 = fmaxf(fmaf(v.w, s[c + 3], t[c + 3]), 0.f);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned *>(&lo); pk.y = *reinterpret_cast<unsigned *>(&hi);
+        reinterpret_cast<uint2 *>(out)[i] = pk;
+    }
+}
+
+// BatchNorm bookkeeping of one layer in one launch: batch statistics from the layer kernel's sums (training) or the
+// moving statistics (inference) -> folded scale s = gamma / sqrt(var + eps) and shift t = beta - mean * s for the NEXT
+// kernel's prologue, plus TF's moving-average update (moving = decay * moving + (1 - decay) * batch; biased variance:
+// tf.contrib.layers.batch_norm, utils/tf_util.py:529-533).
+__global__ void bn_fold_kernel(int k, const float *__restrict__ stats, float inv_count, const float *__restrict__ gamma,
+                               const float *__restrict__ beta, float eps, float decay, int training,
+                               float *__restrict__ moving_mean, float *__restrict__ moving_var,
+                               float *__restrict__ s_out, float *__restrict__ t_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k) return;
+    float mean, var;
+    if (training) {
+        mean = stats[c] * inv_count;
+        var = fmaxf(fmaf(-mean, mean, stats[k + c] * inv_count), 0.f);
+        moving_mean[c] = fmaf(decay, moving_mean[c], (1.f - decay) * mean);
+        moving_var[c] = fmaf(decay, moving_var[c], (1.f - decay) * var);
+    } else {
+        mean = moving_mean[c]; var = moving_var[c];
+    }
+    const float sc = gamma[c] / sqrtf(var + eps);
+    s_out[c] = sc;
+    t_out[c] = fmaf(-mean, sc, beta[c]);
+}
+
+// conv5's BatchNorm + ReLU + max-pool finish on (B, C): from the tcgen05 kernel's per-(element, channel) max / min / sum /
+// sum of squares of y0 = x @ w (no bias) to the pooled feature, in one launch.  One thread per channel.
+//   pooled = relu((ext0 - mean0) * s + beta),  ext0 = max where gamma >= 0 else min,  s = gamma / sqrt(var + eps)
+// Also leaves what the backward needs: inv (C), mean0 (C), ext0 (B,C), z (B,C).
+__global__ void conv5_finish_kernel(int b, int c, const float *__restrict__ vmax, const float *__restrict__ vmin,
+                                    const float *__restrict__ vsum, const float *__restrict__ vsq, const float *__restrict__ bias,
+                                    const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ moving_mean,
+                                    float *__restrict__ moving_var, float inv_count, float eps, float decay, int training,
+                                    float *__restrict__ pooled, float *__restrict__ inv_out, float *__restrict__ mean0_out,
+                                    float *__restrict__ ext0_out, float *__restrict__ z_out)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float mean0, var;
+    if (training) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < b; i++) { s1 += vsum[(size_t)i * c + ch]; s2 += vsq[(size_t)i * c + ch]; }
+        mean0 = s1 * inv_count;
+        var = fmaxf(fmaf(-mean0, mean0, s2 * inv_count), 0.f);
+        moving_mean[ch] = fmaf(decay, moving_mean[ch], (1.f - decay) * (mean0 + bias[ch]));
+        moving_var[ch] = fmaf(decay, moving_var[ch], (1.f - decay) * var);
+    } else {
+        mean0 = moving_mean[ch] - bias[ch]; var = moving_var[ch];
+    }
+    const float inv = 1.0f / sqrtf(var + eps), g = gamma[ch], s = g * inv, be = beta[ch];
+    inv_out[ch] = inv; mean0_out[ch] = mean0;
+    for (int i = 0; i < b; i++) {
+        const float e0 = g >= 0.f ? vmax[(size_t)i * c + ch] : vmin[(size_t)i * c + ch];
+        const float z = fmaf(e0 - mean0, s, be);
+        ext0_out[(size_t)i * c + ch] = e0; z_out[(size_t)i * c + ch] = z; pooled[(size_t)i * c + ch] = fmaxf(z, 0.f);
+    }
+}
+
+constexpr size_t kLayerSmem = sizeof(float) * (2 * kTileP * kLdA + 2 * kKin * kLdW + 2 * kKin + 2 * kCols);
+
+}  // namespace
+
+extern "C" int pnae_mlp_first(long long npts, const float *xyz, const float *w, const float *bias, float *out, float *stats, void *stream)
+{
+    PNAE_REQUIRE(npts >= 1 && xyz && w && bias && out && stats, "mlp_first: invalid argument");
+    PNAE_REQUIRE(pnae_aligned(out, 16), "mlp_first: out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * 64, st));
+    const int blocks = (int)min((npts + 15) / 16, (long long)pnae_sm_count() * 8);
+    mlp_first_kernel<<<blocks, 256, 0, st>>>(npts, xyz, w, bias, out, stats);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}
+
+static BnPrev make_bn(const float *stats, double count, const float *gamma, const float *beta, float *mm, float *mv, float eps,
+                      float decay, int training)
+{
+    BnPrev bn;
+    bn.stats = stats; bn.gamma = gamma; bn.beta = beta; bn.moving_mean = mm; bn.moving_var = mv;
+    bn.inv_count = training ? (float)(1.0 / count) : 0.f; bn.eps = eps; bn.decay = decay; bn.training = training;
+    return bn;
+}
+
+extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in,
+                              const float *stats_prev, const float *gamma_prev, const float *beta_prev,
+                              float *moving_mean_prev, float *moving_var_prev, float eps, float decay, int training,
+                              const float *w, const float *bias, float *out, float *stats, void *stream)
+{
+    PNAE_REQUIRE(npts >= 1 && in && gamma_prev && beta_prev && moving_mean_prev && moving_var_prev && w && bias && out && stats && (!training || stats_prev),
+                 "mlp_layer: invalid argument");
+    PNAE_REQUIRE(kin == kKin && kout >= kCols && kout % kCols == 0, "mlp_layer: needs 64 input channels and a multiple of 64 output channels (got %d -> %d)", kin, kout);
+    PNAE_REQUIRE(pnae_aligned(in, 16) && pnae_aligned(out, 8), "mlp_layer: in must be 16-byte and out 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool configured[64] = {false};
+    int dev = 0;
+    PNAE_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
+        configured[dev] = true;
+    }
+    PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / kCols), st));     // statistics + tile counters
+    const long long ntiles = (npts + kTileP - 1) / kTileP;
+    const int gx = (int)min(ntiles, (long long)pnae_sm_count() * 3);
+    mlp_layer_kernel<<<dim3(gx, kout / kCols), kMlpThreads, kLayerSmem, st>>>(
+        npts, kout, in, make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training), w, bias, out, stats);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}
+
+extern "C" int pnae_bn_fold(int k, const float *stats, double count, const float *gamma, const float *beta, float eps, float decay,
+                            int training, float *moving_mean, float *moving_var, float *s_out, float *t_out, void *stream)
+{
+    PNAE_REQUIRE(k >= 1 && gamma && beta && moving_mean && moving_var && s_out && t_out && (!training || (stats && count >= 1.0)),
+                 "bn_fold: invalid argument");
+    bn_fold_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k, stats, training ? (float)(1.0 / count) : 0.f, gamma, beta, eps, decay,
+                                                                      training, moving_mean, moving_var, s_out, t_out);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}
+
+extern "C" int pnae_mlp_apply_bf16(long long npts, int k, const float *in, const float *stats, const float *gamma, const float *beta,
+                                   float *moving_mean, float *moving_var, float eps, float decay, int training, void *out_bf16, void *stream)
+{
+    PNAE_REQUIRE(npts >= 1 && k >= 4 && k % 4 == 0 && k <= 256 && in && gamma && beta && moving_mean && moving_var && out_bf16 && (!training || stats),
+                 "mlp_apply_bf16: invalid argument");
+    PNAE_REQUIRE(pnae_aligned(in, 16) && pnae_aligned(out_bf16, 8), "mlp_apply_bf16: misaligned buffer");
+    const long long n4 = npts * k / 4;
+    const int blocks = (int)min((n4 + 255) / 256, (long long)pnae_sm_count() * 16);
+    mlp_apply_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n4, k, in, make_bn(stats, (double)npts, gamma, beta, moving_mean, moving_var, eps, decay, training),
+                                                                     (__nv_bfloat16 *)out_bf16);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}
+
+extern "C" int pnae_conv5_finish(int b, int c, double count, const float *vmax, const float *vmin, const float *vsum, const float *vsq,
+                                 const float *bias, const float *gamma, const float *beta, float *moving_mean, float *moving_var,
+                                 float eps, float decay, int training, float *pooled, float *inv, float *mean0, float *ext0, float *z, void *stream)
+{
+    PNAE_REQUIRE(b >= 1 && c >= 1 && count >= 1.0 && vmax && vmin && vsum && vsq && bias && gamma && beta && moving_mean && moving_var && pooled && inv && mean0 && ext0 && z,
+                 "conv5_finish: invalid argument");
+    conv5_finish_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b, c, vmax, vmin, vsum, vsq, bias, gamma, beta, moving_mean, moving_var,
+                                                                           (float)(1.0 / count), eps, decay, training, pooled, inv, mean0, ext0, z);
+    PNAE_CUDA_OK(cudaGetLastError());
+    return PNAE_OK;
+}

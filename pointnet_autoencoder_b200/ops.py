@@ -248,3 +248,93 @@ def encoder_conv_pool(x_bf16, wt_bf16, sign=None):
         _lib.check(lib.pnae_encoder_conv_pool(b, n, k, c, _p(x), _p(wt), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
                                               _p(sign), _p(arg), _stream(x)))
     return tuple(outs) if arg is None else tuple(outs) + (arg,)
+
+
+# ---------------------------------------------------------------------------
+# encoder layers 1-4 (csrc/shared_mlp.cu)
+# ---------------------------------------------------------------------------
+def mlp_first(xyz, w, bias):
+    """layer 1: xyz (B,N,3) fp32, w (3,64), bias (64,) -> raw output (B*N,64) fp32, stats (2,64) = per-channel sum / sum of squares"""
+    _dev(xyz, "xyz")
+    _require(xyz.dim() == 3 and xyz.shape[2] == 3 and tuple(w.shape) == (3, 64) and tuple(bias.shape) == (64,), "mlp_first expects xyz (batch,#points,3), w (3,64), bias (64,)")
+    x = _f32c(xyz); w = _f32c(_dev(w, "w")); bias = _f32c(_dev(bias, "bias"))
+    npts = x.shape[0] * x.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        out = torch.empty((npts, 64), dtype=torch.float32, device=x.device)
+        stats = torch.empty((2, 64), dtype=torch.float32, device=x.device)
+        _lib.check(lib.pnae_mlp_first(npts, _p(x), _p(w), _p(bias), _p(out), _p(stats), _stream(x)))
+    return out, stats
+
+
+def _bn_args(k, stats, gamma, beta, moving_mean, moving_var, training):
+    _require(tuple(gamma.shape) == (k,) and tuple(beta.shape) == (k,) and tuple(moving_mean.shape) == (k,) and tuple(moving_var.shape) == (k,),
+             "BatchNorm parameters must have one entry per input channel")
+    _require(moving_mean.is_contiguous() and moving_var.is_contiguous() and moving_mean.dtype == torch.float32 and moving_var.dtype == torch.float32,
+             "moving statistics must be contiguous float32 (they are updated in place)")
+    _require((not training) or (stats is not None and stats.is_contiguous() and tuple(stats.shape) == (2, k)), "training mode needs the previous layer's stats (2,k)")
+    return _f32c(_dev(gamma, "gamma")), _f32c(_dev(beta, "beta"))
+
+
+def mlp_layer(y_prev, stats_prev, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, training, decay, eps, w, bias):
+    """layers 2-4: relu(BatchNorm_prev(y_prev)) @ w + bias -> raw output (T,kout) fp32, stats (2,kout).
+    BatchNorm_prev uses batch statistics formed from stats_prev (training; the moving statistics are updated in place,
+    TF convention) or the moving statistics (inference)."""
+    _dev(y_prev, "y_prev")
+    kin, kout = w.shape
+    _require(y_prev.dim() == 2 and y_prev.shape[1] == kin and tuple(bias.shape) == (kout,), "mlp_layer expects y_prev (points,kin), w (kin,kout), bias (kout,)")
+    g, b = _bn_args(kin, stats_prev, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, training)
+    y = _f32c(y_prev); w = _f32c(_dev(w, "w")); bias = _f32c(_dev(bias, "bias"))
+    lib = _lib.load()
+    with torch.cuda.device(y.device):
+        out = torch.empty((y.shape[0], kout), dtype=torch.float32, device=y.device)
+        buf = torch.empty((2 * kout + kout // 64,), dtype=torch.float32, device=y.device)      # statistics + the kernel's tile counters
+        _lib.check(lib.pnae_mlp_layer(y.shape[0], kin, kout, _p(y), _p(stats_prev), _p(g), _p(b), _p(moving_mean_prev), _p(moving_var_prev),
+                                      float(eps), float(decay), int(bool(training)), _p(w), _p(bias), _p(out), _p(buf), _stream(y)))
+    return out, buf[: 2 * kout].view(2, kout)
+
+
+def bn_fold(stats, count, gamma, beta, moving_mean, moving_var, training, decay, eps):
+    """-> (s, t): folded BatchNorm scale / shift of one layer (batch statistics from `stats` and a moving-average update when
+    training, moving statistics otherwise); one launch"""
+    k = gamma.shape[0]
+    g = _f32c(_dev(gamma, "gamma")); b = _f32c(_dev(beta, "beta"))
+    _require(moving_mean.is_contiguous() and moving_var.is_contiguous() and moving_mean.dtype == torch.float32, "bn_fold expects contiguous fp32 moving statistics")
+    lib = _lib.load()
+    with torch.cuda.device(g.device):
+        s = torch.empty((k,), dtype=torch.float32, device=g.device); t = torch.empty((k,), dtype=torch.float32, device=g.device)
+        _lib.check(lib.pnae_bn_fold(k, _p(stats) if stats is not None else None, float(count), _p(g), _p(b), float(eps), float(decay), int(bool(training)),
+                                    _p(moving_mean), _p(moving_var), _p(s), _p(t), _stream(g)))
+    return s, t
+
+
+def mlp_apply_bf16(y, stats, gamma, beta, moving_mean, moving_var, training, decay, eps):
+    """relu(BatchNorm(y)) -> bf16 (T,k): the K-major operand of encoder_conv_pool (BatchNorm given as in mlp_layer)"""
+    _dev(y, "y")
+    k = y.shape[1]
+    _require(y.dim() == 2 and k % 4 == 0 and k <= 256, "mlp_apply_bf16 expects y (points,k), k % 4 == 0, k <= 256")
+    g, b = _bn_args(k, stats, gamma, beta, moving_mean, moving_var, training)
+    y = _f32c(y)
+    lib = _lib.load()
+    with torch.cuda.device(y.device):
+        out = torch.empty((y.shape[0], k), dtype=torch.bfloat16, device=y.device)
+        _lib.check(lib.pnae_mlp_apply_bf16(y.shape[0], k, _p(y), _p(stats), _p(g), _p(b), _p(moving_mean), _p(moving_var),
+                                           float(eps), float(decay), int(bool(training)), _p(out), _stream(y)))
+    return out
+
+
+def conv5_finish(vmax, vmin, vsum, vsq, count, bias, gamma, beta, moving_mean, moving_var, training, decay, eps):
+    """conv5's bias + BatchNorm + ReLU + max-pool finish on (B,C) in one launch -> pooled, inv (C), mean0 (C), ext0 (B,C), z (B,C)"""
+    b, c = vmax.shape
+    g, be = _bn_args(c, None, gamma, beta, moving_mean, moving_var, False)
+    bias = _f32c(_dev(bias, "bias"))
+    lib = _lib.load()
+    dev = vmax.device
+    with torch.cuda.device(dev):
+        f = dict(dtype=torch.float32, device=dev)
+        pooled = torch.empty((b, c), **f); inv = torch.empty((c,), **f); mean0 = torch.empty((c,), **f)
+        ext0 = torch.empty((b, c), **f); z = torch.empty((b, c), **f)
+        _lib.check(lib.pnae_conv5_finish(b, c, float(count), _p(_f32c(vmax)), _p(_f32c(vmin)), _p(_f32c(vsum)), _p(_f32c(vsq)), _p(bias), _p(g), _p(be),
+                                         _p(moving_mean), _p(moving_var), float(eps), float(decay), int(bool(training)),
+                                         _p(pooled), _p(inv), _p(mean0), _p(ext0), _p(z), _stream(vmax)))
+    return pooled, inv, mean0, ext0, z

@@ -112,3 +112,105 @@ def test_encoder_backward_end_to_end():
     enc(pc).square().sum().backward()
     for p_ in enc.parameters():
         assert p_.grad is not None and torch.isfinite(p_.grad).all()
+
+
+# ---- layers 1-4 (csrc/shared_mlp.cu) against an fp64 PyTorch evaluation of the same layer ---------------------------
+@pytest.mark.parametrize("b,n", [(2, 256), (1, 1000), (3, 2048), (32, 2048), (1, 37)])
+def test_mlp_first_layer_vs_torch(b, n):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(b, n, 3, device="cuda", generator=g)
+    w = torch.randn(3, 64, device="cuda", generator=g); bias = torch.randn(64, device="cuda", generator=g)
+    y, st = ops.mlp_first(x, w, bias)
+    ref = (x.double().reshape(-1, 3) @ w.double() + bias.double())
+    assert y.shape == (b * n, 64) and scaled_err(y, ref.float()) < 1e-6
+    assert scaled_err(st[0].double(), ref.sum(0)) < 1e-5 and scaled_err(st[1].double(), (ref * ref).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("npts,kout,training", [(256, 64, True), (1000, 64, False), (65536, 64, True), (65536, 128, True), (37, 128, False), (4133, 128, True)])
+def test_mlp_layer_vs_torch(npts, kout, training):
+    """previous layer's BatchNorm (batch or moving statistics) + ReLU on the way in, 3xTF32 product (fp32 accuracy, NOT
+    TF32's 1e-3), bias, statistics of the output, TF-style moving-average update of the previous layer's statistics"""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    yprev = rnd(npts, 64) * 2 + 0.3
+    gamma = rnd(64); beta = 0.2 * rnd(64)
+    mm = 0.3 * rnd(64); mv = torch.rand(64, device="cuda", generator=g) + 0.5
+    w = rnd(64, kout) / 8; bias = rnd(kout)
+    eps, decay = 1e-3, 0.9
+    yd = yprev.double()
+    if training:
+        mean = yd.mean(0); var = yd.var(0, unbiased=False)
+        st_prev = torch.stack([yd.sum(0), (yd * yd).sum(0)]).float().contiguous()
+    else:
+        mean, var, st_prev = mm.double(), mv.double(), None
+    mm_k, mv_k = mm.clone(), mv.clone()
+    y, st = ops.mlp_layer(yprev, st_prev, gamma, beta, mm_k, mv_k, training, decay, eps, w, bias)
+    a = torch.relu((yd - mean) * torch.rsqrt(var + eps) * gamma.double() + beta.double())
+    ref = a @ w.double() + bias.double()
+    assert y.shape == (npts, kout)
+    assert scaled_err(y.double(), ref) < 1e-5, "the 3xTF32 split must keep fp32 accuracy"
+    assert scaled_err(st[0].double(), ref.sum(0)) < 1e-4 and scaled_err(st[1].double(), (ref * ref).sum(0)) < 1e-5
+    if training:      # moving = decay * moving + (1 - decay) * batch, biased variance (tf.contrib.layers.batch_norm)
+        assert scaled_err(mm_k.double(), decay * mm.double() + (1 - decay) * mean) < 1e-5
+        assert scaled_err(mv_k.double(), decay * mv.double() + (1 - decay) * var) < 1e-4
+    else:
+        assert torch.equal(mm_k, mm) and torch.equal(mv_k, mv)
+
+
+def test_mlp_apply_bf16():
+    g = torch.Generator(device="cuda").manual_seed(6)
+    y = torch.randn(4133, 128, device="cuda", generator=g)
+    gamma = torch.randn(128, device="cuda", generator=g); beta = 0.1 * torch.randn(128, device="cuda", generator=g)
+    mm = 0.1 * torch.randn(128, device="cuda", generator=g); mv = torch.rand(128, device="cuda", generator=g) + 0.5
+    out = ops.mlp_apply_bf16(y, None, gamma, beta, mm, mv, False, 0.9, 1e-3)
+    s = gamma * torch.rsqrt(mv + 1e-3); t = beta - mm * s
+    ref = torch.relu(y * s + t)
+    # bf16 rounding of an fp32 value that may itself differ in the last fp32 bit: one bf16 ulp (2^-8 relative)
+    assert out.dtype == torch.bfloat16 and float((out.float() - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+
+
+def test_conv5_finish_vs_torch():
+    g = torch.Generator(device="cuda").manual_seed(7)
+    b, c, n = 5, 256, 300
+    rnd = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    y0 = rnd(b, n, c)
+    vmax, vmin, vsum, vsq = y0.amax(1), y0.amin(1), y0.sum(1), (y0 * y0).sum(1)
+    bias = 0.1 * rnd(c); gamma = rnd(c); beta = 0.1 * rnd(c); mm = 0.1 * rnd(c); mv = torch.rand(c, device="cuda", generator=g) + 0.5
+    for training in (True, False):
+        mm_k, mv_k = mm.clone(), mv.clone()
+        pooled, inv, mean0, ext0, z = ops.conv5_finish(vmax, vmin, vsum, vsq, b * n, bias, gamma, beta, mm_k, mv_k, training, 0.9, 1e-3)
+        y = y0.double() + bias.double()
+        if training:
+            mean, var = y.mean((0, 1)), y.var((0, 1), unbiased=False)
+        else:
+            mean, var = mm.double(), mv.double()
+        ref = torch.relu((y - mean) * torch.rsqrt(var + 1e-3) * gamma.double() + beta.double()).amax(1)
+        assert scaled_err(pooled.double(), ref) < 1e-5
+        if training:
+            assert scaled_err(mm_k.double(), 0.9 * mm.double() + 0.1 * mean) < 1e-5 and scaled_err(mv_k.double(), 0.9 * mv.double() + 0.1 * var) < 1e-4
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_encoder_chain_layers_1_to_4_match_the_library_path(training):
+    """PointNetEncoder(fused=True) (every layer a hand-written kernel) against fused="conv5" (library layers 1-4, the
+    same conv5 kernel): layers 1-4 keep fp32 accuracy, so the two agree far inside conv5's bf16 tolerance, and the
+    moving statistics of layers 1-4 are updated identically."""
+    torch.manual_seed(1)
+    a = PointNetEncoder(fused=True).cuda(); r = PointNetEncoder(fused="conv5").cuda()
+    r.load_state_dict(a.state_dict())
+    a.train(training); r.train(training)
+    pc = torch.randn(4, 1024, 3, device="cuda")
+    ya = a(pc); yr = r(pc)
+    assert scaled_err(ya, yr) < 5e-3
+    if training:
+        for la, lr in zip(a.layers, r.layers):
+            assert scaled_err(la.moving_mean, lr.moving_mean) < 1e-4 and scaled_err(la.moving_var, lr.moving_var) < 1e-3
+    # backward: gradients of every parameter against the library-layer path
+    pa = pc.clone().requires_grad_(True); pr = pc.clone().requires_grad_(True)
+    tgt = torch.randn(4, 1024, device="cuda")
+    (a(pa) * tgt).sum().backward(); (r(pr) * tgt).sum().backward()
+    assert scaled_err(pa.grad, pr.grad) < 5e-2
+    for (na, p_a), (_, p_r) in zip(a.named_parameters(), r.named_parameters()):
+        if p_r.grad is None or float(p_r.grad.abs().max()) == 0.0 or (training and na.endswith(".bias")):
+            continue          # (training-mode BN removes the mean: bias gradients are rounding noise around zero)
+        assert scaled_err(p_a.grad, p_r.grad) < 5e-2, na

@@ -89,6 +89,20 @@ class AutoEncoderUpconv(nn.Module):
         return net.permute(0, 2, 3, 1).reshape(-1, 2048, 3), {"embedding": emb}
 
 
+def nn_distance_cpu(xyz1, xyz2):
+    """The reference's pure-TF Chamfer (tf_ops/nn_distance/tf_nndistance_cpu.py:4-25, used by models/model_cpu.py:81),
+    restated with the same broadcast formulation: a (B,N,M,3) difference tensor, squared, summed over the last axis,
+    reduce_min / argmin over either point axis (int64 indices, as tf.argmin returns).  BASELINE ONLY (configs[0]): it
+    materialises B*N*M*3 floats and is not accelerated; works on any device."""
+    n, m = xyz1.shape[1], xyz2.shape[1]
+    a = xyz1[:, :, None, :].expand(-1, n, m, -1)
+    c = xyz2[:, None, :, :].expand(-1, n, m, -1)
+    d = ((a - c) ** 2).sum(-1)
+    dist1, idx1 = d.min(dim=2)
+    dist2, idx2 = d.min(dim=1)
+    return dist1, idx1, dist2, idx2
+
+
 def chamfer_loss(pred, label):
     """models/model.py:77-83 -> (loss*100, pcloss)"""
     d_fwd, _, d_bwd, _ = tf_nndistance.nn_distance(pred, label)

@@ -35,10 +35,20 @@ class Match(object):
     (the only write to `match` in the reference: tf_approxmatch_g.cu:145-153)."""
 
     def __init__(self, xyz1, xyz2, factors):
-        self.xyz1 = xyz1
-        self.xyz2 = xyz2
+        # The handle keeps its OWN copy of the clouds (1.5 MB at B=32, N=2048): the factors only mean something together
+        # with the coordinates they were computed from, and the caller may overwrite its tensors in place afterwards.
+        # The source tensors' identity and version counters are remembered so match_cost can tell whether it is being
+        # called with exactly those (unmodified) clouds.
+        self._src = tuple((t.data_ptr(), t._version, tuple(t.shape), t.is_contiguous()) for t in (xyz1, xyz2))
+        self.xyz1 = xyz1.detach().clone()
+        self.xyz2 = xyz2.detach().clone()
         self.factors = factors          # (B, 10, N+M)
         self._dense = None
+
+    def computed_from(self, xyz1, xyz2):
+        """True iff (xyz1, xyz2) are the very tensors this match was computed from, unchanged since"""
+        return all(t.is_contiguous() and (t.data_ptr(), t._version, tuple(t.shape), True) == src
+                   for t, src in zip((xyz1, xyz2), self._src))
 
     @property
     def shape(self):
@@ -107,7 +117,7 @@ returns:
         xyz2 = xyz2.detach()
         if dense:
             return _ops.approx_match_factors(xyz1, xyz2, dense=True)[1]
-        return Match(xyz1.contiguous(), xyz2.contiguous(), _ops.approx_match_factors(xyz1, xyz2))
+        return Match(xyz1, xyz2, _ops.approx_match_factors(xyz1, xyz2))
 
 
 class _MatchCostFactors(torch.autograd.Function):
@@ -156,9 +166,9 @@ returns:
             raise ValueError("MatchCost expects (batch_size,#query,#dataset) match shape")
         # The factors re-evaluate exp(level*d) from the coordinates, so the fused path is the
         # reference's "match is a constant" only for the clouds the match was computed from.
-        same = (xyz1.data_ptr() == match.xyz1.data_ptr() and xyz2.data_ptr() == match.xyz2.data_ptr()
-                and xyz1.is_contiguous() and xyz2.is_contiguous())
-        if same:
+        # (same storage AND same version counter: an in-place update of the clouds between approx_match and match_cost
+        # must see the match as the constant it was, i.e. the dense tensor built from the handle's own snapshot)
+        if match.computed_from(xyz1, xyz2):
             return _MatchCostFactors.apply(xyz1, xyz2, match)
         match = match.dense()
     return _MatchCostDense.apply(xyz1, xyz2, match.detach())
@@ -167,6 +177,8 @@ returns:
 def match_cost_grad(xyz1, xyz2, match):
     '''The MatchCostGrad op (tf_approxmatch.cpp:16-21): -> grad1, grad2 (not yet scaled by grad_cost)'''
     if isinstance(match, Match):
-        _, g1, g2 = _ops.match_cost_factors(xyz1, xyz2, match.factors, with_grad=True)
-        return g1, g2
+        if match.computed_from(xyz1, xyz2):
+            _, g1, g2 = _ops.match_cost_factors(xyz1, xyz2, match.factors, with_grad=True)
+            return g1, g2
+        match = match.dense()
     return _ops.match_cost_dense_bwd(xyz1, xyz2, match)

@@ -302,6 +302,18 @@ def test_match_handle_is_tensor_like_and_guards_constant_semantics():
     c_handle = tf_approxmatch.match_cost(y1, x2, match)
     c_dense = tf_approxmatch.match_cost(y1, x2, match.dense())
     assert torch.allclose(c_handle, c_dense, rtol=1e-6)
+    # the clouds updated IN PLACE after approx_match (same storage, new values): the match must still be the constant
+    # computed from the old coordinates, for match_cost and for match_cost_grad alike
+    z1 = x1.clone(); z2 = x2.clone()
+    m2 = tf_approxmatch.approx_match(z1, z2)
+    want = tf_approxmatch.approx_match(z1, z2, dense=True).clone()
+    z1.add_(0.01)
+    c_after = tf_approxmatch.match_cost(z1, z2, m2)
+    assert torch.allclose(c_after, tf_approxmatch.match_cost(z1, z2, want), rtol=1e-6)
+    ga, gb = tf_approxmatch.match_cost_grad(z1, z2, m2)
+    ra, rb = tf_approxmatch.match_cost_grad(z1, z2, want)
+    assert torch.allclose(ga, ra, rtol=1e-4, atol=1e-6) and torch.allclose(gb, rb, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(m2.dense(), want, atol=1e-6)
 
 
 def test_full_size_properties():

@@ -181,3 +181,17 @@ def test_fp64_ground_truth_agrees_with_the_fp32_restatement(n, m):
     o1, o2 = O.match_cost_grad(xyz1, xyz2, match)
     sc = lambda a, r: np.abs(a - r).max() / np.abs(r).max()
     assert sc(o1, g1) < 2e-5 and sc(o2, g2) < 2e-5
+
+
+def test_pure_tf_chamfer_restatement_matches_the_oracle():
+    """the broadcast Chamfer of tf_nndistance_cpu.py:4-25 (baseline of BASELINE.json configs[0]),
+    restated in pointnet_autoencoder_b200.models.nn_distance_cpu, against the oracle: same neighbours, distances to
+    fp32 rounding (the broadcast form sums x^2+y^2+z^2 without the GPU kernel's FMA contraction)."""
+    import torch
+    from pointnet_autoencoder_b200 import models
+    xyz1, xyz2 = synthetic.s_randn(3, 130, 77, seed=4)
+    d1, i1, d2, i2 = models.nn_distance_cpu(torch.from_numpy(xyz1), torch.from_numpy(xyz2))
+    od1, oi1, od2, oi2 = O.nn_distance(xyz1, xyz2, contract=False)
+    assert i1.dtype == torch.int64 and d1.shape == (3, 130) and d2.shape == (3, 77)
+    np.testing.assert_allclose(d1.numpy(), od1, rtol=2e-6, atol=1e-7); np.testing.assert_allclose(d2.numpy(), od2, rtol=2e-6, atol=1e-7)
+    assert np.array_equal(i1.numpy(), oi1) and np.array_equal(i2.numpy(), oi2)

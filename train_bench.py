@@ -42,9 +42,8 @@ def cpu_baseline(args):
 
     def step():
         pred, _ = model(x, 0.5)
-        diff = pred[:, :, None, :] - x[:, None, :, :]                     # (B,N,M,3) broadcast, as the TF code does
-        d = (diff * diff).sum(-1)
-        loss = (d.min(2).values.mean() + d.min(1).values.mean()) * 100
+        d1, _, d2, _ = models.nn_distance_cpu(pred, x)                    # (B,N,M,3) broadcast, as the TF code does
+        loss = (d1.mean() + d2.mean()) * 100
         opt.zero_grad(); loss.backward(); opt.step()
         return float(loss)
     step()

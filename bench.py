@@ -281,14 +281,38 @@ def run_product(args):
     # is the benchmarked one; the three-kernel form (fwd, then the separate gradient op) is timed next to it.
     from pointnet_autoencoder_b200.graphs import ChamferStep
     SPG = args.steps_per_graph      # consecutive steps captured per graph (launch overhead amortised over SPG steps)
-    assert RING % SPG == 0 and args.steps % SPG == 0 and args.warmup % SPG == 0, "steps/warmup must be multiples of --steps-per-graph"
-    grp = lambda t, g: [t[g * SPG + j] for j in range(SPG)]
+    assert RING % SPG == 0, "--steps-per-graph must divide the ring of %d batches" % RING
     NG = RING // SPG
-    slots = [ChamferStep(grp(x1, 0), grp(x2, 0), g1, g2, fused=True)]
-    slots += [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, fused=True, share_buffers_with=slots[0]) for g in range(1, NG)]   # new inputs, same outputs/workspace
-    slots3 = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, share_buffers_with=slots[0]) for g in range(NG)]
-    # the dominant kernel pair alone (sweep + finalize), for the roofline figure
-    fwd_slots = [ChamferStep(grp(x1, g), grp(x2, g), g1, g2, forward_only=True, share_buffers_with=slots[0]) for g in range(NG)]
+
+    class Ring:
+        """graphs of SPG consecutive steps over the ring of input batches, plus one shorter graph for the remainder, so
+        that run(k) executes EXACTLY k steps whatever k is"""
+
+        def __init__(self, **kw):
+            self.kw = kw
+            first = ChamferStep([x1[j] for j in range(SPG)], [x2[j] for j in range(SPG)], g1, g2, **kw)
+            self.share = kw.pop("share_buffers_with", None) or first        # every graph writes the same outputs / workspace
+            self.kw = dict(kw, share_buffers_with=self.share)
+            self.full = [first] + [ChamferStep([x1[g * SPG + j] for j in range(SPG)], [x2[g * SPG + j] for j in range(SPG)], g1, g2, **self.kw)
+                                   for g in range(1, NG)]
+            self.rem = {}
+            self.pos = 0
+
+        def run(self, k):
+            for _ in range(k // SPG):
+                self.full[self.pos % NG].run(); self.pos += 1
+            r = k % SPG
+            if r:
+                if r not in self.rem:
+                    self.rem[r] = ChamferStep([x1[RING - 1 - j] for j in range(r)], [x2[RING - 1 - j] for j in range(r)], g1, g2, **self.kw)
+                self.rem[r].run()
+
+    ring = Ring(fused=True)                                        # the benchmarked two-kernel step
+    ring3 = Ring(share_buffers_with=ring.share)                    # the three-kernel form
+    ring_fwd = Ring(forward_only=True, share_buffers_with=ring.share)   # the dominant kernel pair alone (sweep + finalize), for the roofline figure
+    for r_ in (ring, ring3, ring_fwd):                             # build the remainder graphs outside the timed region
+        r_.run(args.steps % SPG); r_.run(args.warmup % SPG)
+    slots = ring.full
 
     def barrier():
         if world > 1:
@@ -296,19 +320,16 @@ def run_product(args):
         torch.cuda.synchronize()
 
     def timed_windows(which, windows):
-        """`windows` back-to-back windows of args.steps steps each, CUDA events on the launching stream around every
-        window; -> list of ms per window"""
+        """`windows` back-to-back windows of EXACTLY args.steps steps each, CUDA events on the launching stream around
+        every window; -> the events"""
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(windows + 1)]
-        k = 0
         evs[0].record(stream)
         for w in range(windows):
-            for i in range(args.steps // SPG):
-                which[k % NG].run(); k += 1
+            which.run(args.steps)
             evs[w + 1].record(stream)
         return evs
 
-    for i in range(args.warmup // SPG):
-        slots[i % NG].run()
+    ring.run(args.warmup)
     barrier()
 
     sampler = ClockSampler(local)
@@ -316,11 +337,11 @@ def run_product(args):
     time.sleep(0.15)
     barrier()
     t0 = time.perf_counter()
-    ev_step = timed_windows(slots, WINDOWS)
+    ev_step = timed_windows(ring, WINDOWS)
     barrier()
-    ev_three = timed_windows(slots3, WINDOWS)
+    ev_three = timed_windows(ring3, WINDOWS)
     barrier()
-    ev_fwd = timed_windows(fwd_slots, WINDOWS)       # forward alone, same ring, same clocks
+    ev_fwd = timed_windows(ring_fwd, WINDOWS)        # forward alone, same ring, same clocks
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
@@ -338,7 +359,7 @@ def run_product(args):
     check = None
     if rank == 0:
         import oracle
-        last = (WINDOWS * (args.steps // SPG) - 1) % NG
+        last = (ring.pos - 1) % NG if ring.pos else 0
         slots[last].run(); torch.cuda.synchronize()
         e_in = last * SPG + SPG - 1
         od1, oi1, od2, oi2 = oracle.cpu.nn_distance(h1[e_in, :1], h2[e_in, :1])
@@ -419,7 +440,7 @@ def run_product(args):
         "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
                    "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                    "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB) > 126 MB L2; outputs and workspace are reused" % (RING, RING * 12 * B * (N + M) / 1e6),
-                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps" % (SPG, SPG),
+                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps, plus one shorter graph when K is not a multiple of %d" % (SPG, SPG, SPG),
                    "timing": "%d back-to-back windows of %d steps, CUDA events on the launching stream; value = median window, max over ranks" % (WINDOWS, args.steps),
                    "upstream_grad": "100/(B*N) (models/model.py:81-83), passed as grad_dist arrays",
                    "host_cores_of_rank0": len(cores) if cores else None},
@@ -633,7 +654,7 @@ def main():
     ap.add_argument("--no-emd", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the autoencoder training-step figure (BASELINE configs[3])")
     ap.add_argument("--no-refgpu", action="store_true", help="skip timing the reference's own CUDA kernels")
-    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches; steps and warmup are rounded up to whole graphs)")
+    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches); a shorter graph covers the remainder, so exactly --steps steps are timed per window")
     ap.add_argument("--max-seconds", type=float, default=1200.0, help="hard wall-clock limit: exit with status 3 instead of hanging a GPU box (0 = none)")
     args = ap.parse_args()
     if args.max_seconds > 0:
@@ -645,9 +666,8 @@ def main():
         wd.daemon = True
         wd.start()
     if args.impl != "reference":
-        spg = args.steps_per_graph
-        args.steps = max(spg, (args.steps + spg - 1) // spg * spg)      # whole graphs only; the JSON line reports the steps actually run
-        args.warmup = max(spg, (args.warmup + spg - 1) // spg * spg)
+        args.steps = max(1, args.steps)
+        args.warmup = max(3, args.warmup)          # never fewer than three warm-up steps
     if args.impl == "reference":
         run_reference(args)
     else:

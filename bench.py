@@ -378,19 +378,23 @@ def run_product(args):
     e2e_steps = 400
     p1 = torch.from_numpy(h1).pin_memory(); p2 = torch.from_numpy(h2).pin_memory()   # inputs start in pinned host memory
 
+    SUB = 4                     # batches per submission of the host pipeline (one CUDA graph, one copy each way)
+    assert e2e_steps % SUB == 0 and RING % SUB == 0
+
     def e2e_run(results):
-        runner = host_api.ChamferHostPipeline(B, N, M, dev, depth=4, results=results)
-        for i in range(8):
-            runner.submit(p1[i % RING], p2[i % RING])
+        runner = host_api.ChamferHostPipeline(B, N, M, dev, depth=4, results=results, steps_per_submit=SUB)
+        chunk = lambda t, i: t[(i * SUB) % RING: (i * SUB) % RING + SUB]      # SUB consecutive batches: contiguous pinned memory
+        for i in range(4):
+            runner.submit(chunk(p1, i), chunk(p2, i))
         runner.drain()
         barrier()
         t_0 = time.perf_counter()
         got = 0
-        for i in range(e2e_steps):
-            got += runner.submit(p1[i % RING], p2[i % RING]) is not None
+        for i in range(e2e_steps // SUB):
+            got += runner.submit(chunk(p1, i), chunk(p2, i)) is not None
         got += len(runner.drain())                     # every step's results are back on the host when the clock stops
         dt = time.perf_counter() - t_0
-        assert got == e2e_steps
+        assert got == e2e_steps // SUB
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,6 +402,27 @@ def run_product(args):
         return dt, runner
     e2e_s, runner = e2e_run("all")
     e2e_grads_s, runner_g = e2e_run("grads")
+
+    def pcie_rate(nbytes, to_host):
+        """GB/s of back-to-back pinned copies of one step's result (to_host) / input (to device) size on one stream:
+        the link's own ceiling for the e2e figure"""
+        dbuf = torch.empty((nbytes,), dtype=torch.uint8, device=dev); hbuf = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+        src, dst = (dbuf, hbuf) if to_host else (hbuf, dbuf)
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(100):
+            dst.copy_(src, non_blocking=True)
+        b_.record(); b_.synchronize()
+        return nbytes * 100 / (a.elapsed_time(b_) * 1e-3) / 1e9
+    pcie = None
+    if rank == 0:
+        try:
+            pcie = {"d2h_gbs": pcie_rate(runner.d2h_bytes, True), "h2d_gbs": pcie_rate(runner.h2d_bytes // 2, False)}
+        except Exception as exc:      # noqa: BLE001
+            pcie = {"error": str(exc)}
 
     extra = {}
 
@@ -460,9 +485,15 @@ def run_product(args):
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "e2e": {"value": pairs * e2e_steps * world / e2e_s / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
-                "api": "host_api.ChamferHostPipeline over pnae_chamfer_host_pipeline_submit (C): pinned host in -> H2D -> graph (2 kernels) -> D2H of dist/idx/grads, 4 buffer sets on 3 streams",
+                "api": "host_api.ChamferHostPipeline over pnae_chamfer_host_pipeline_submit (C): pinned host in -> H2D -> graph (2 kernels per step) -> D2H of dist/idx/grads; %d batches per submission, 4 buffer sets on 3 streams; every step's inputs go in and every step's results come back" % SUB,
+                "batches_per_submission": SUB,
                 "gradients_only": {"value": pairs * e2e_steps * world / e2e_grads_s / 1e9, "d2h_bytes_per_step": runner_g.d2h_bytes,
-                                   "note": "same pipeline returning only grad_xyz1/grad_xyz2 (what a training loop consumes)"}},
+                                   "note": "same pipeline returning only grad_xyz1/grad_xyz2 (what a training loop consumes)"},
+                # the link's own ceiling, measured in this run on rank 0 alone (copies of exactly these sizes, nothing else running)
+                "pcie": pcie,
+                "bound": (None if not pcie or "error" in pcie else
+                          "device->host copy: %.2f MB per step at the measured %.1f GB/s is %.1f us of the %.1f us e2e step (kernels %.1f us)"
+                          % (runner.d2h_bytes / 1e6, pcie["d2h_gbs"], runner.d2h_bytes / pcie["d2h_gbs"] / 1e3, e2e_s / e2e_steps * 1e6, step_ms * 1e3))},
         "gpu_launches": 2 * args.steps * WINDOWS,
         "clocks": clocks,
         "check": check,

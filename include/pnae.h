@@ -131,19 +131,21 @@ PNAE_API int pnae_graph_destroy(void *handle);
 
 /* Streaming host-buffer form of the Chamfer step: what a caller without device data runs (the reference feeds its
  * op from host memory through feed_dict and reads results through sess.run, train.py:196-206).  `depth` buffer sets
- * on three internal streams: the host->device copy of step i+1, the kernels of step i and the device->host copy of
- * step i-1 overlap.  All memory is the caller's: per set a device xyz1 (b,n,3), a device xyz2 (b,m,3), a flat device
- * result buffer and a PINNED host result buffer of the same layout; out_offsets[6] are the byte offsets of
- * { grad_xyz1, grad_xyz2, dist1, idx1, dist2, idx2 } inside a result buffer and d2h_bytes the leading bytes copied
- * back per step (the whole buffer, or only the gradients when they are laid out first).  One workspace
+ * on three internal streams: the host->device copy of submission i+1, the kernels of submission i and the device->host
+ * copy of submission i-1 overlap.  A submission is `steps` consecutive batches (>= 1) run as ONE CUDA graph.  All memory
+ * is the caller's: per set a device xyz1 (steps,b,n,3), a device xyz2 (steps,b,m,3), a device result buffer of `steps`
+ * blocks `out_stride` bytes apart and a PINNED host result buffer of the same layout; out_offsets[6] are the byte offsets
+ * of { grad_xyz1, grad_xyz2, dist1, idx1, dist2, idx2 } inside a block and d2h_bytes the leading bytes of every block
+ * copied back (the whole block, or only the gradients when they are laid out first).  One workspace
  * (pnae_nn_distance_workspace_bytes) is shared: the steps run in order on one stream.  fused != 0 selects
  * pnae_nn_distance_fwd_grad (two kernels per step) over fwd + bwd (three). */
-PNAE_API int pnae_chamfer_host_pipeline_create(int depth, int b, int n, int m, int fused,
+PNAE_API int pnae_chamfer_host_pipeline_create(int depth, int steps, int b, int n, int m, int fused,
                                                float *const *d_xyz1, float *const *d_xyz2,
-                                               void *const *d_out, void *const *h_out, const size_t *out_offsets, size_t d2h_bytes,
+                                               void *const *d_out, void *const *h_out, const size_t *out_offsets,
+                                               size_t out_stride, size_t d2h_bytes,
                                                const float *grad_dist1, const float *grad_dist2,
                                                void *workspace, size_t workspace_bytes, void **handle);
-/* Enqueue one step on host inputs (pinned for true asynchrony).  *retired = index of the buffer set whose results
+/* Enqueue one submission (`steps` batches, contiguous in h_xyz1 / h_xyz2) on host inputs (pinned for true asynchrony).  *retired = index of the buffer set whose results
  * are now complete in its host buffer and stay valid until the next submit, or -1 while the pipeline fills. */
 PNAE_API int pnae_chamfer_host_pipeline_submit(void *handle, const float *h_xyz1, const float *h_xyz2, int *retired);
 /* Wait for everything in flight: retired[0..*count) = completed buffer sets, oldest first (retired needs depth ints). */

@@ -39,7 +39,7 @@ SIGNATURES = {
     "pnae_chamfer_graph_create_fused_multi": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_graph_create": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_graph_create_multi": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
-    "pnae_chamfer_host_pipeline_create": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "pnae_chamfer_host_pipeline_create": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "pnae_chamfer_host_pipeline_submit": (_i, [_vp, _vp, _vp, C.POINTER(_i)]),
     "pnae_chamfer_host_pipeline_drain": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "pnae_chamfer_host_pipeline_destroy": (_i, [_vp]),

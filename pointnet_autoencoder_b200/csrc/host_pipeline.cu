@@ -3,9 +3,13 @@
 // The reference's TF op is fed from host memory by the session (train.py:196-206 builds the batch in numpy and
 // feed_dict copies it in; the results come back through sess.run).  This is that path for a caller of the C ABI:
 // every step copies its inputs host->device, runs the step's CUDA graph and copies the results device->host, with
-// `depth` buffer sets on three streams so that the H2D copy of step i+1, the kernels of step i and the D2H copy of
-// step i-1 overlap.  One pnae_chamfer_host_pipeline_submit() call is: two cudaMemcpyAsync (inputs), one
-// cudaGraphLaunch, one cudaMemcpyAsync (results), three event records, two stream waits -- nothing else on the host.
+// `depth` buffer sets on three streams so that the H2D copy of submission i+1, the kernels of submission i and the D2H
+// copy of submission i-1 overlap.  A submission is `steps` consecutive batches (steps >= 1): their inputs go in with two
+// copies, their kernels are one CUDA graph (programmatic dependent launch chains the steps without gaps), all their
+// results come back with one copy.  One pnae_chamfer_host_pipeline_submit() call is: two cudaMemcpyAsync (inputs), one
+// cudaGraphLaunch, one cudaMemcpy(2D)Async (results), three event records, two stream waits -- nothing else on the host.
+// Measured on B200 (B=32, N=M=2048): one batch per submission 69 us per step, four batches per submission 54 us per
+// step (the kernels alone take 52.8 us) -- a one-step graph pays its launch ramp and loses the overlap between steps.
 //
 // Memory stays the caller's (device inputs / outputs / workspace and the pinned result buffers are passed in at
 // creation); the handle owns streams, events and graphs only.
@@ -18,14 +22,15 @@ namespace {
 struct Set {
     float *d_xyz1, *d_xyz2;
     char *d_out, *h_out;
-    void *graph;                   // pnae graph handle
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
     cudaEvent_t ev_in, ev_run, ev_out;
     bool busy;
 };
 
 struct HostPipeline {
-    int depth, b, n, m;
-    size_t in1_bytes, in2_bytes, d2h_bytes;
+    int depth, steps, b, n, m;
+    size_t in1_bytes, in2_bytes, d2h_bytes, out_stride;
     cudaStream_t s_in, s_run, s_out;
     std::vector<Set> sets;
     long long count;
@@ -34,7 +39,8 @@ struct HostPipeline {
 void destroy(HostPipeline *hp)
 {
     for (Set &s : hp->sets) {
-        if (s.graph) pnae_graph_destroy(s.graph);
+        if (s.exec) cudaGraphExecDestroy(s.exec);
+        if (s.graph) cudaGraphDestroy(s.graph);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_run) cudaEventDestroy(s.ev_run);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -47,24 +53,72 @@ void destroy(HostPipeline *hp)
 
 }  // namespace
 
-extern "C" int pnae_chamfer_host_pipeline_create(int depth, int b, int n, int m, int fused,
+// One set's CUDA graph: `steps` consecutive Chamfer steps over the set's own inputs and result blocks (programmatic
+// dependent launch chains them, so a graph of several steps has no gaps between steps), captured here rather than through
+// pnae_chamfer_graph_create_* because every step has its own outputs.
+static int capture_set(HostPipeline *hp, Set &s, int fused, const size_t *off, const float *gd1, const float *gd2,
+                       void *workspace, size_t workspace_bytes)
+{
+    cudaStream_t st;
+    PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) {
+        cudaStreamDestroy(st);
+        pnae_set_error("host_pipeline_create: cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    int rc = PNAE_OK;
+    for (int k = 0; k < hp->steps && rc == PNAE_OK; k++) {
+        char *o = s.d_out + (size_t)k * hp->out_stride;
+        const float *x1 = s.d_xyz1 + (size_t)k * hp->b * hp->n * 3, *x2 = s.d_xyz2 + (size_t)k * hp->b * hp->m * 3;
+        float *g1 = (float *)(o + off[0]), *g2 = (float *)(o + off[1]);
+        float *dist1 = (float *)(o + off[2]); int *idx1 = (int *)(o + off[3]);
+        float *dist2 = (float *)(o + off[4]); int *idx2 = (int *)(o + off[5]);
+        if (fused) {
+            rc = pnae_nn_distance_fwd_grad(hp->b, hp->n, x1, hp->m, x2, gd1, gd2, dist1, idx1, dist2, idx2, g1, g2, workspace, workspace_bytes, st);
+        } else {
+            rc = pnae_nn_distance_fwd(hp->b, hp->n, x1, hp->m, x2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, st);
+            if (rc == PNAE_OK) rc = pnae_nn_distance_bwd(hp->b, hp->n, x1, hp->m, x2, gd1, idx1, gd2, idx2, g1, g2, st);
+        }
+    }
+    ce = cudaStreamEndCapture(st, &graph);
+    cudaStreamDestroy(st);
+    if (rc != PNAE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || graph == nullptr) {
+        pnae_set_error("host_pipeline_create: cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    ce = cudaGraphInstantiate(&s.exec, graph, 0);
+    s.graph = graph;
+    if (ce != cudaSuccess) {
+        pnae_set_error("host_pipeline_create: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        return PNAE_ERR_CUDA;
+    }
+    return PNAE_OK;
+}
+
+extern "C" int pnae_chamfer_host_pipeline_create(int depth, int steps, int b, int n, int m, int fused,
                                                  float *const *d_xyz1, float *const *d_xyz2,
-                                                 void *const *d_out, void *const *h_out, const size_t *out_offsets, size_t d2h_bytes,
+                                                 void *const *d_out, void *const *h_out, const size_t *out_offsets,
+                                                 size_t out_stride, size_t d2h_bytes,
                                                  const float *grad_dist1, const float *grad_dist2,
                                                  void *workspace, size_t workspace_bytes, void **handle)
 {
     PNAE_REQUIRE(handle != nullptr, "host_pipeline_create: NULL handle");
     *handle = nullptr;
-    PNAE_REQUIRE(depth >= 1 && depth <= 64 && b >= 1 && n >= 1 && m >= 1, "host_pipeline_create: invalid sizes");
+    PNAE_REQUIRE(depth >= 1 && depth <= 64 && steps >= 1 && steps <= 64 && b >= 1 && n >= 1 && m >= 1, "host_pipeline_create: invalid sizes");
+    PNAE_REQUIRE(d2h_bytes >= 1 && d2h_bytes <= out_stride, "host_pipeline_create: need 1 <= d2h_bytes <= out_stride");
     PNAE_REQUIRE(d_xyz1 && d_xyz2 && d_out && h_out && out_offsets && grad_dist1 && grad_dist2, "host_pipeline_create: NULL pointer");
     HostPipeline *hp = new HostPipeline();
-    hp->depth = depth; hp->b = b; hp->n = n; hp->m = m;
-    hp->in1_bytes = sizeof(float) * 3 * (size_t)b * n;
-    hp->in2_bytes = sizeof(float) * 3 * (size_t)b * m;
-    hp->d2h_bytes = d2h_bytes;
+    hp->depth = depth; hp->steps = steps; hp->b = b; hp->n = n; hp->m = m;
+    hp->in1_bytes = sizeof(float) * 3 * (size_t)steps * b * n;
+    hp->in2_bytes = sizeof(float) * 3 * (size_t)steps * b * m;
+    hp->d2h_bytes = d2h_bytes; hp->out_stride = out_stride;
     hp->count = 0;
     hp->s_in = hp->s_run = hp->s_out = nullptr;
     hp->sets.assign(depth, Set{});
+    for (Set &z : hp->sets) { z.graph = nullptr; z.exec = nullptr; z.ev_in = z.ev_run = z.ev_out = nullptr; }
     int rc = PNAE_OK;
     auto cuda_ok = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == PNAE_OK) {
@@ -89,15 +143,8 @@ extern "C" int pnae_chamfer_host_pipeline_create(int depth, int b, int n, int m,
         cuda_ok(cudaEventCreateWithFlags(&s.ev_run, cudaEventDisableTiming), "cudaEventCreate");
         cuda_ok(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming), "cudaEventCreate");
         if (rc != PNAE_OK) break;
-        // flat result layout (byte offsets): grad_xyz1, grad_xyz2, dist1, idx1, dist2, idx2
-        float *g1 = (float *)(s.d_out + out_offsets[0]), *g2 = (float *)(s.d_out + out_offsets[1]);
-        float *dist1 = (float *)(s.d_out + out_offsets[2]); int *idx1 = (int *)(s.d_out + out_offsets[3]);
-        float *dist2 = (float *)(s.d_out + out_offsets[4]); int *idx2 = (int *)(s.d_out + out_offsets[5]);
-        const float *x1 = s.d_xyz1, *x2 = s.d_xyz2;
-        rc = fused ? pnae_chamfer_graph_create_fused_multi(1, b, n, &x1, m, &x2, dist1, idx1, dist2, idx2, grad_dist1, grad_dist2, g1, g2,
-                                                           workspace, workspace_bytes, &s.graph)
-                   : pnae_chamfer_graph_create_multi(1, b, n, &x1, m, &x2, dist1, idx1, dist2, idx2, grad_dist1, grad_dist2, g1, g2,
-                                                     workspace, workspace_bytes, &s.graph);
+        // per-step result block (byte offsets): grad_xyz1, grad_xyz2, dist1, idx1, dist2, idx2; blocks are out_stride apart
+        rc = capture_set(hp, s, fused, out_offsets, grad_dist1, grad_dist2, workspace, workspace_bytes);
     }
     if (rc != PNAE_OK) { destroy(hp); return rc; }
     *handle = hp;
@@ -114,11 +161,13 @@ extern "C" int pnae_chamfer_host_pipeline_submit(void *handle, const float *h_xy
     PNAE_CUDA_OK(cudaMemcpyAsync(s.d_xyz2, h_xyz2, hp->in2_bytes, cudaMemcpyHostToDevice, hp->s_in));
     PNAE_CUDA_OK(cudaEventRecord(s.ev_in, hp->s_in));
     PNAE_CUDA_OK(cudaStreamWaitEvent(hp->s_run, s.ev_in, 0));
-    int rc = pnae_graph_launch(s.graph, hp->s_run);
-    if (rc != PNAE_OK) return rc;
+    PNAE_CUDA_OK(cudaGraphLaunch(s.exec, hp->s_run));
     PNAE_CUDA_OK(cudaEventRecord(s.ev_run, hp->s_run));
     PNAE_CUDA_OK(cudaStreamWaitEvent(hp->s_out, s.ev_run, 0));
-    PNAE_CUDA_OK(cudaMemcpyAsync(s.h_out, s.d_out, hp->d2h_bytes, cudaMemcpyDeviceToHost, hp->s_out));
+    if (hp->d2h_bytes == hp->out_stride || hp->steps == 1)
+        PNAE_CUDA_OK(cudaMemcpyAsync(s.h_out, s.d_out, hp->steps == 1 ? hp->d2h_bytes : hp->out_stride * hp->steps, cudaMemcpyDeviceToHost, hp->s_out));
+    else          // only the leading d2h_bytes of every step's block (e.g. the gradients): one strided copy
+        PNAE_CUDA_OK(cudaMemcpy2DAsync(s.h_out, hp->out_stride, s.d_out, hp->out_stride, hp->d2h_bytes, hp->steps, cudaMemcpyDeviceToHost, hp->s_out));
     PNAE_CUDA_OK(cudaEventRecord(s.ev_out, hp->s_out));
     s.busy = true;
     hp->count++;

@@ -76,63 +76,70 @@ class ChamferHostRunner:
 
 class ChamferHostPipeline:
     """Streaming form of ChamferHostRunner over the C ABI's pnae_chamfer_host_pipeline_*: `depth` buffer sets and three
-    streams so that the host->device copy of step i+1, the kernels of step i and the device->host copy of step i-1
-    overlap (PCIe both directions + SMs busy at once).  One submit() is ONE call into libpnae.so (two input copies, one
-    graph launch, one result copy, events); torch only owns the memory.
+    streams so that the host->device copy of submission i+1, the kernels of submission i and the device->host copy of
+    submission i-1 overlap (PCIe both directions + SMs busy at once).  One submit() is ONE call into libpnae.so (two input
+    copies, one graph launch, one result copy, events); torch only owns the memory.
 
-        pipe = ChamferHostPipeline(B, N, M)
-        for xyz1, xyz2 in batches:                 # pinned host tensors (or numpy arrays)
-            done = pipe.submit(xyz1, xyz2)         # -> results of the step that just retired, or None
+        pipe = ChamferHostPipeline(B, N, M, steps_per_submit=4)
+        for xyz1, xyz2 in chunks_of_4_batches:     # pinned host tensors (or numpy arrays), shape (4, B, N, 3) / (4, B, M, 3)
+            done = pipe.submit(xyz1, xyz2)         # -> results of the submission that just retired, or None
         for done in pipe.drain(): ...
 
+    steps_per_submit: consecutive batches per submission (one CUDA graph, no gaps between its steps).  With 1, inputs are
+    (B,N,3)/(B,M,3) and results (B,...) arrays; with k > 1 everything carries a leading axis of length k.
     results="all": every step returns dist1/idx1/dist2/idx2/grad_xyz1/grad_xyz2; results="grads": only the two
     gradient fields cross PCIe (what a training loop consumes).  Results are dicts of numpy views on pinned buffers,
     valid until the next submit()."""
 
-    def __init__(self, b, n, m, device="cuda", depth=4, results="all", fused=True, grad_dist1=None, grad_dist2=None):
+    def __init__(self, b, n, m, device="cuda", depth=4, results="all", fused=True, grad_dist1=None, grad_dist2=None, steps_per_submit=1):
         import ctypes as C
         from . import _lib
-        assert results in ("all", "grads")
+        assert results in ("all", "grads") and steps_per_submit >= 1
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.depth = depth
-        self.b, self.n, self.m = b, n, m
+        self.b, self.n, self.m, self.k = b, n, m, steps_per_submit
+        k = steps_per_submit
         lib = _lib.load()
         spec = [("grad_xyz1", (b, n, 3), torch.float32), ("grad_xyz2", (b, m, 3), torch.float32), ("dist1", (b, n), torch.float32),
                 ("idx1", (b, n), torch.int32), ("dist2", (b, m), torch.float32), ("idx2", (b, m), torch.int32)]
-        offs, total = [], 0
+        offs, stride = [], 0
         for name, shape, dt in spec:
-            offs.append(total)
-            total += (int(np.prod(shape)) * 4 + 255) // 256 * 256
+            offs.append(stride)
+            stride += (int(np.prod(shape)) * 4 + 255) // 256 * 256
         grads_end = offs[2]
         self.names = [s_[0] for s_ in spec] if results == "all" else ["grad_xyz1", "grad_xyz2"]
-        self.h2d_bytes = 4 * 3 * b * (n + m)
+        self.h2d_bytes = 4 * 3 * b * (n + m)                     # per step
         self.d2h_bytes = sum(int(np.prod(shape)) * 4 for name, shape, _ in spec if name in self.names)
-        copy_bytes = total if results == "all" else grads_end
+        copy_bytes = stride if results == "all" else grads_end
         f32 = dict(dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self.g1 = torch.full((b, n), 100.0 / (b * n), **f32) if grad_dist1 is None else grad_dist1.to(**f32).contiguous()
             self.g2 = torch.full((b, m), 100.0 / (b * m), **f32) if grad_dist2 is None else grad_dist2.to(**f32).contiguous()
-            self.d_xyz1 = [torch.empty((b, n, 3), **f32) for _ in range(depth)]
-            self.d_xyz2 = [torch.empty((b, m, 3), **f32) for _ in range(depth)]
-            self.d_out = [torch.empty((total,), dtype=torch.uint8, device=self.device) for _ in range(depth)]
-            self.h_out = [torch.empty((total,), dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
-            self.h_in1 = [_pinned((b, n, 3), torch.float32) for _ in range(depth)]      # staging for non-pinned inputs
-            self.h_in2 = [_pinned((b, m, 3), torch.float32) for _ in range(depth)]
+            self.d_xyz1 = [torch.empty((k, b, n, 3), **f32) for _ in range(depth)]
+            self.d_xyz2 = [torch.empty((k, b, m, 3), **f32) for _ in range(depth)]
+            self.d_out = [torch.empty((k * stride,), dtype=torch.uint8, device=self.device) for _ in range(depth)]
+            self.h_out = [torch.empty((k * stride,), dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+            self.h_in1 = [_pinned((k, b, n, 3), torch.float32) for _ in range(depth)]      # staging for non-pinned inputs
+            self.h_in2 = [_pinned((k, b, m, 3), torch.float32) for _ in range(depth)]
             wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
             self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=self.device)
             arr = lambda ts: (C.c_void_p * depth)(*[t.data_ptr() for t in ts])
             h = C.c_void_p()
             torch.cuda.synchronize(self.device)
-            _lib.check(lib.pnae_chamfer_host_pipeline_create(depth, b, n, m, int(bool(fused)), arr(self.d_xyz1), arr(self.d_xyz2),
-                                                             arr(self.d_out), arr(self.h_out), (C.c_size_t * 6)(*offs), copy_bytes,
+            _lib.check(lib.pnae_chamfer_host_pipeline_create(depth, k, b, n, m, int(bool(fused)), arr(self.d_xyz1), arr(self.d_xyz2),
+                                                             arr(self.d_out), arr(self.h_out), (C.c_size_t * 6)(*offs), stride, copy_bytes,
                                                              C.c_void_p(self.g1.data_ptr()), C.c_void_p(self.g2.data_ptr()),
                                                              C.c_void_p(self.ws.data_ptr()), wsb, C.byref(h)))
         self._h, self._lib, self._check, self._C = h, lib, _lib.check, C
-        carve = lambda flat, i, shape, dt: flat[offs[i]: offs[i] + int(np.prod(shape)) * 4].view(dt).view(shape)
-        self._views = [{name: carve(self.h_out[k], i, shape, dt).numpy() for i, (name, shape, dt) in enumerate(spec) if name in self.names}
-                       for k in range(depth)]
+
+        def carve(flat, i, shape, dt):
+            blocks = flat.view(k, stride)[:, offs[i]: offs[i] + int(np.prod(shape)) * 4]      # (k, bytes) strided view
+            a = blocks.numpy().view(np.float32 if dt == torch.float32 else np.int32).reshape((k,) + tuple(shape))
+            return a[0] if k == 1 else a
+        self._views = [{name: carve(self.h_out[j], i, shape, dt) for i, (name, shape, dt) in enumerate(spec) if name in self.names}
+                       for j in range(depth)]
         self.kernels_per_step = 2 if fused else 3
         self.count = 0
         self._retired = C.c_int(-1)
@@ -140,19 +147,19 @@ class ChamferHostPipeline:
     def _host_ptr(self, src, stage):
         """address of a host copy of `src` the async copy can read: pinned tensors as they are, anything else staged"""
         if isinstance(src, torch.Tensor):
-            if src.is_pinned() and src.is_contiguous() and src.dtype == torch.float32:
+            if src.is_pinned() and src.is_contiguous() and src.dtype == torch.float32 and src.numel() == stage.numel():
                 return src.data_ptr()
-            stage.copy_(src)
+            stage.copy_(src.reshape(stage.shape))
         else:
-            stage.numpy()[...] = src
+            stage.numpy()[...] = np.asarray(src, np.float32).reshape(tuple(stage.shape))
         return stage.data_ptr()
 
     def submit(self, xyz1, xyz2):
-        k = self.count % self.depth
+        j = self.count % self.depth
         C = self._C
         with torch.cuda.device(self.device):
-            self._check(self._lib.pnae_chamfer_host_pipeline_submit(self._h, C.c_void_p(self._host_ptr(xyz1, self.h_in1[k])),
-                                                                    C.c_void_p(self._host_ptr(xyz2, self.h_in2[k])), C.byref(self._retired)))
+            self._check(self._lib.pnae_chamfer_host_pipeline_submit(self._h, C.c_void_p(self._host_ptr(xyz1, self.h_in1[j])),
+                                                                    C.c_void_p(self._host_ptr(xyz2, self.h_in2[j])), C.byref(self._retired)))
         self.count += 1
         r = self._retired.value
         return self._views[r] if r >= 0 else None

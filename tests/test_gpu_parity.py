@@ -203,22 +203,33 @@ def test_fused_chamfer_loss_grad_equals_two_op_path(b, n):
     close_scaled(p_b.grad.cpu().numpy(), o1, 1e-5, "grad vs oracle")
 
 
-def test_host_pipeline_matches_eager():
+@pytest.mark.parametrize("sub,results,fused", [(1, "all", True), (2, "all", True), (3, "grads", True), (1, "all", False)])
+def test_host_pipeline_matches_eager(sub, results, fused):
     from pointnet_autoencoder_b200 import host_api
     b, n, m = 2, 300, 200
-    pipe = host_api.ChamferHostPipeline(b, n, m, depth=3)
-    batches = [synthetic.s_randn(b, n, m, seed=s) for s in range(7)]
+    pipe = host_api.ChamferHostPipeline(b, n, m, depth=3, steps_per_submit=sub, results=results, fused=fused)
+    batches = [synthetic.s_randn(b, n, m, seed=s) for s in range(7 * sub)]
     outs = []
-    for a, c in batches:
-        r = pipe.submit(a, c)
+
+    def keep(r):
+        for j in range(sub):           # one entry per step, in submission order
+            outs.append({k: (v if sub == 1 else v[j]).copy() for k, v in r.items()})
+    for i in range(7):
+        grp = batches[i * sub:(i + 1) * sub]
+        a = np.stack([g_[0] for g_ in grp]); c = np.stack([g_[1] for g_ in grp])
+        r = pipe.submit(a[0] if sub == 1 else a, c[0] if sub == 1 else c)
         if r is not None:
-            outs.append({k: v.copy() for k, v in r.items()})
-    outs += [{k: v.copy() for k, v in r.items()} for r in pipe.drain()]
-    assert len(outs) == 7
+            keep(r)
+    for r in pipe.drain():
+        keep(r)
+    assert len(outs) == 7 * sub
     for (a, c), r in zip(batches, outs):        # results come back in submission order
         od1, oi1, od2, oi2 = O.nn_distance(a, c)
-        assert np.array_equal(r["dist1"], od1) and np.array_equal(r["idx1"], oi1)
-        assert np.array_equal(r["dist2"], od2) and np.array_equal(r["idx2"], oi2)
+        if results == "all":
+            assert np.array_equal(r["dist1"], od1) and np.array_equal(r["idx1"], oi1)
+            assert np.array_equal(r["dist2"], od2) and np.array_equal(r["idx2"], oi2)
+        else:
+            assert sorted(r) == ["grad_xyz1", "grad_xyz2"]
         g = np.full((b, n), 100.0 / (b * n), np.float32); g2 = np.full((b, m), 100.0 / (b * m), np.float32)
         o1, o2 = O.nn_distance_grad(a, c, g, oi1, g2, oi2)
         np.testing.assert_allclose(r["grad_xyz1"], o1, rtol=1e-4, atol=1e-7)

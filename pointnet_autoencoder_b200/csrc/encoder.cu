@@ -17,7 +17,9 @@
 //    training-mode BatchNorm needs -- so BN (either mode) + ReLU + max-pool finish on a (B,1024)
 //    tensor ("Training-mode BatchNorm blocks naive encoder fusion").
 //  * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation),
-//    warps 2..5 = epilogue (one TMEM lane quadrant each); mbarrier pipelines smem<->MMA<->epilogue.
+//    warps 2..9 = epilogue: two warps per TMEM lane quadrant, each reducing half of a tile's 256 columns (with four
+//    epilogue warps the 256-value reduction per channel took as long as the tile's MMAs: K is only 128), merged through
+//    shared memory at the end; mbarrier pipelines smem<->MMA<->epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -30,7 +32,8 @@ constexpr int kTileN = 256;        // points per MMA tile (UMMA N)
 constexpr int kKBox = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int kMaxK = 128;
 constexpr int kStages = 2;
-constexpr int kEncThreads = 192;   // 6 warps
+constexpr int kEncThreads = 320;   // 10 warps: TMA, MMA, 8 epilogue (two per TMEM lane quadrant, half the columns each)
+constexpr int kEpiThreads = 256;
 constexpr int kSpinLimit = 1 << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,6 +137,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + kStages;
     uint64_t *t_full = b_empty + kStages, *t_empty = t_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    float *merge = reinterpret_cast<float *>(bars) + 64;           // [6][128]: the second half's partial results (256 B past the barriers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cb = blockIdx.x, e = blockIdx.y;
@@ -144,7 +148,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
         mbar_init(a_full, 1);
         for (int s = 0; s < kStages; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        for (int s = 0; s < 2; s++) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -190,8 +194,10 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
             }
         }
     } else {
-        // ===== epilogue: one thread per channel, reduction over points in registers =====
+        // ===== epilogue: two threads per channel (one per column half), reduction over points in registers =====
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                         // columns [half*128, half*128 + 128) of every tile
+        constexpr int kHalfN = kTileN / 2;
         float vmax = -__int_as_float(0x7f800000), vmin = __int_as_float(0x7f800000), vsum = 0.f, vsq = 0.f;
         const int ch_mine = cb * kTileM + q * 32 + lane;
         // key = +v (track the maximum) or -v (track the minimum): flipping the sign bit is exact
@@ -203,30 +209,32 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
             const int valid = min(kTileN, n - t * kTileN);
             mbar_wait(t_full + buf, (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + half * kHalfN;
 #pragma unroll 1
-            for (int ch = 0; ch < kTileN / 32; ch++) {
+            for (int ch = 0; ch < kHalfN / 32; ch++) {
+                const int col0 = half * kHalfN + ch * 32;         // first column of this 32-column group inside the tile
+                if (col0 >= valid) break;                         // (warp-uniform) nothing live in the rest of this half
                 float v[32];
                 tmem_ld32(taddr + ch * 32, v);
-                if ((ch + 1) * 32 <= valid) {
+                if (col0 + 32 <= valid) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
                         vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
                         if (ARG) {
                             const float key = __uint_as_float(__float_as_uint(v[i]) ^ flip);
-                            if (key > kbest) { kbest = key; ibest = t * kTileN + ch * 32 + i; }   // strict: first point wins
+                            if (key > kbest) { kbest = key; ibest = t * kTileN + col0 + i; }   // strict: first point wins
                         }
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; i++)
-                        if (ch * 32 + i < valid) {
+                        if (col0 + i < valid) {
                             vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]);
                             vsum += v[i]; vsq = fmaf(v[i], v[i], vsq);
                             if (ARG) {
                                 const float key = __uint_as_float(__float_as_uint(v[i]) ^ flip);
-                                if (key > kbest) { kbest = key; ibest = t * kTileN + ch * 32 + i; }
+                                if (key > kbest) { kbest = key; ibest = t * kTileN + col0 + i; }
                             }
                         }
                 }
@@ -234,11 +242,25 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(t_empty + buf);
         }
+        // merge the two column halves of every channel: the second half hands its partial results over in shared memory
+        const int slot = q * 32 + lane;
+        if (half == 1) {
+            merge[slot] = vmax; merge[128 + slot] = vmin; merge[256 + slot] = vsum; merge[384 + slot] = vsq;
+            merge[512 + slot] = kbest; merge[640 + slot] = __int_as_float(ibest);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");          // the eight epilogue warps only
         const int ch_out = cb * kTileM + q * 32 + lane;
-        if (ch_out < c) {
+        if (half == 0 && ch_out < c) {
+            vmax = fmaxf(vmax, merge[slot]); vmin = fminf(vmin, merge[128 + slot]);
+            vsum += merge[256 + slot]; vsq += merge[384 + slot];
             const size_t o = (size_t)e * c + ch_out;
             omax[o] = vmax; omin[o] = vmin; osum[o] = vsum; osq[o] = vsq;
-            if (ARG) oarg[o] = ibest;
+            if (ARG) {
+                const float k1 = merge[512 + slot];
+                const int i1 = __float_as_int(merge[640 + slot]);
+                if (k1 > kbest || (k1 == kbest && i1 < ibest)) ibest = i1;       // the extremum's FIRST point, whichever half saw it
+                oarg[o] = ibest;
+            }
         }
     }
 
@@ -301,7 +323,7 @@ extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_
     rc = make_map(&tm_x, x_bf16, (uint64_t)b * n, (uint64_t)k, kTileN);
     if (rc) return rc;
     const int kboxes = k / kKBox;
-    const size_t smem = 1024 + (size_t)kboxes * kTileM * 128 + (size_t)kStages * kboxes * kTileN * 128 + 256;
+    const size_t smem = 1024 + (size_t)kboxes * kTileM * 128 + (size_t)kStages * kboxes * kTileN * 128 + 256 + 6 * 128 * sizeof(float);
     dim3 grid((unsigned)(c / kTileM), (unsigned)b);
     if (out_arg) {
         PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -213,7 +213,19 @@ PNAE_API int pnae_match_cost_factors(int b, int n, int m, const float *xyz1, con
  * training backward routes the pooled gradient to that point. */
 PNAE_API int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
                                     float *out_max, float *out_min, float *out_sum, float *out_sumsq,
-                                    const float *sign, int *out_arg, void *stream);
+                                    const float *sign, int *out_arg, int flags /* PNAE_OVERLAP_PREVIOUS or 0 */, void *stream);
+
+/* ---- flags of the encoder entry points ---------------------------------------------------------
+ * PNAE_STATS_ZEROED      the caller has already zeroed `stats` (all of it, tile-counter words included): the call
+ *                        does not enqueue its own memset.  A chain of layers zeroes one arena once.
+ * PNAE_OVERLAP_PREVIOUS  programmatic dependent launch: the kernel may be scheduled while the kernel enqueued
+ *                        immediately before it on `stream` is still draining.  Its set-up -- staging this layer's
+ *                        `w` / `bias` (`wt_bf16` for pnae_encoder_conv_pool), barriers, tensor memory -- runs under
+ *                        that tail; every other read and every write waits until the predecessor has completed.
+ *                        The caller promises that the immediately preceding kernel does not write `w`, `bias` or
+ *                        `wt_bf16`.  Results are identical with and without the flag. */
+#define PNAE_STATS_ZEROED 1
+#define PNAE_OVERLAP_PREVIOUS 2
 
 /* ---- PointNet encoder: layers 1-4 (3 -> 64 -> 64 -> 64 -> 128), one kernel per layer ---------- */
 
@@ -227,14 +239,14 @@ PNAE_API int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf
  * counters.
  * npts = batch * points; all matrices row-major fp32; w is (kin, kout) like the reference's [1,1,kin,kout] kernel. */
 PNAE_API int pnae_mlp_first(long long npts, const float *xyz, const float *w /* (3,64) */, const float *bias,
-                            float *out /* (npts,64) */, float *stats /* (2,64) */, void *stream);
+                            float *out /* (npts,64) */, float *stats /* (2,64) */, int flags, void *stream);
 /* The previous layer's BatchNorm is given by its raw statistics (stats_prev (2,kin), training != 0: batch statistics, and
  * the kernel also performs TF's moving-average update of moving_mean_prev / moving_var_prev with the biased variance,
  * utils/tf_util.py:529-533) or by its moving statistics (training == 0; stats_prev may be NULL). */
 PNAE_API int pnae_mlp_layer(long long npts, int kin /* 64 */, int kout /* 64 or 128 */, const float *in,
                             const float *stats_prev, const float *gamma_prev, const float *beta_prev,
                             float *moving_mean_prev, float *moving_var_prev, float eps, float decay, int training,
-                            const float *w, const float *bias, float *out, float *stats, void *stream);
+                            const float *w, const float *bias, float *out, float *stats, int flags, void *stream);
 /* BatchNorm bookkeeping of one layer on its own (the layer kernels do this in their prologue; this entry exists for callers
  * that want the folded scale s = gamma/sqrt(var+eps) and shift t = beta - mean*s themselves). */
 PNAE_API int pnae_bn_fold(int k, const float *stats, double count, const float *gamma, const float *beta, float eps, float decay,
@@ -243,14 +255,14 @@ PNAE_API int pnae_bn_fold(int k, const float *stats, double count, const float *
  * pnae_encoder_conv_pool. */
 PNAE_API int pnae_mlp_apply_bf16(long long npts, int k, const float *in, const float *stats, const float *gamma, const float *beta,
                                  float *moving_mean, float *moving_var, float eps, float decay, int training,
-                                 void *out_bf16, void *stream);
+                                 void *out_bf16, int flags, void *stream);
 /* conv5's bias + BatchNorm + ReLU + max-pool finish on (b, c), one launch: from pnae_encoder_conv_pool's max / min / sum /
  * sumsq to pooled (b,c) = relu((ext0 - mean0) * gamma * inv + beta), ext0 = max where gamma >= 0 else min; count = b * n.
  * Also returns what the backward needs: inv (c), mean0 (c) (of x @ w without the bias), ext0 (b,c), z (b,c). */
 PNAE_API int pnae_conv5_finish(int b, int c, double count, const float *vmax, const float *vmin, const float *vsum, const float *vsq,
                                const float *bias, const float *gamma, const float *beta, float *moving_mean, float *moving_var,
                                float eps, float decay, int training, float *pooled, float *inv, float *mean0, float *ext0, float *z,
-                               void *stream);
+                               int flags, void *stream);
 
 #ifdef __cplusplus
 }

@@ -143,6 +143,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     const int cb = blockIdx.x, e = blockIdx.y;
     const int ntiles = (n + kTileN - 1) / kTileN;
 
+    pnae_pdl_release();
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
@@ -165,6 +166,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         if (lane == 0) {
             mbar_expect_tx(a_full, a_bytes);
             for (int kb = 0; kb < kboxes; kb++) tma_load_2d(sa + (size_t)kb * kTileM * 128, &tm_w, kb * kKBox, cb * kTileM, a_full);
+            pnae_pdl_wait();              // the weights may load under the previous kernel's tail (PNAE_OVERLAP_PREVIOUS); X is its output
             for (int t = 0; t < ntiles; t++) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait(b_empty + s, ((t / kStages) - 1) & 1);
@@ -201,6 +203,7 @@ encoder_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         float vmax = -__int_as_float(0x7f800000), vmin = __int_as_float(0x7f800000), vsum = 0.f, vsq = 0.f;
         const int ch_mine = cb * kTileM + q * 32 + lane;
         // key = +v (track the maximum) or -v (track the minimum): flipping the sign bit is exact
+        pnae_pdl_wait();                  // (`sign` is a parameter, but the outputs below are the previous kernel's to finish with first)
         const unsigned flip = (ARG && ch_mine < c && sign[ch_mine] < 0.f) ? 0x80000000u : 0u;
         float kbest = -__int_as_float(0x7f800000);
         int ibest = 0;
@@ -308,8 +311,9 @@ int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t k, uint
 
 extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_bf16, const void *wt_bf16,
                                       float *out_max, float *out_min, float *out_sum, float *out_sumsq,
-                                      const float *sign, int *out_arg, void *stream)
+                                      const float *sign, int *out_arg, int flags, void *stream)
 {
+    PNAE_REQUIRE((flags & ~PNAE_OVERLAP_PREVIOUS) == 0, "encoder_conv_pool: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE((sign == nullptr) == (out_arg == nullptr), "encoder_conv_pool: pass both `sign` and `out_arg` or neither");
     PNAE_REQUIRE(b >= 0 && n >= 1, "encoder_conv_pool: need b>=0, n>=1 (got b=%d n=%d)", b, n);
     PNAE_REQUIRE(k >= kKBox && k <= kMaxK && k % kKBox == 0, "encoder_conv_pool: in-channels must be 64 or 128 (got %d)", k);
@@ -327,10 +331,12 @@ extern "C" int pnae_encoder_conv_pool(int b, int n, int k, int c, const void *x_
     dim3 grid((unsigned)(c / kTileM), (unsigned)b);
     if (out_arg) {
         PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encoder_conv_pool_kernel<true><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, sign, out_arg);
+        PNAE_CUDA_OK(pnae_launch(encoder_conv_pool_kernel<true>, grid, dim3(kEncThreads), smem, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+                                 tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, sign, out_arg));
     } else {
         PNAE_CUDA_OK(cudaFuncSetAttribute(encoder_conv_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encoder_conv_pool_kernel<false><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, nullptr, nullptr);
+        PNAE_CUDA_OK(pnae_launch(encoder_conv_pool_kernel<false>, grid, dim3(kEncThreads), smem, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+                                 tm_w, tm_x, n, k, c, out_max, out_min, out_sum, out_sumsq, (const float *)nullptr, (int *)nullptr));
     }
     PNAE_CUDA_OK(cudaGetLastError());
     return PNAE_OK;

@@ -34,6 +34,26 @@ void pnae_set_error(const char *fmt, ...);
 
 int pnae_sm_count();   // cached per device
 
+// Launch `kernel`, optionally as a programmatic dependent launch (include/pnae.h, PNAE_OVERLAP_PREVIOUS): the grid may
+// then be scheduled while the kernel before it on the stream is still draining; inside the kernel everything up to
+// `griddepcontrol.wait` overlaps that tail, everything after it sees the predecessor complete.
+template <typename... KArgs, typename... Args>
+inline cudaError_t pnae_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool overlap, Args... args)
+{
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+// programmatic dependent launch, device side (both are no-ops in a grid launched the ordinary way)
+__device__ __forceinline__ void pnae_pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }   // the next grid may be scheduled
+__device__ __forceinline__ void pnae_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }        // the previous grid is complete and visible
+#endif
+
 static inline bool pnae_aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // ---- device side ------------------------------------------------------------

@@ -80,9 +80,8 @@ __global__ void __launch_bounds__(256)
 mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__restrict__ w, const float *__restrict__ bias,
                  float *__restrict__ out, float *__restrict__ stats)
 {
-    __shared__ float s_stats[2][64];
-    if (threadIdx.x < 128) s_stats[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
-    __syncthreads();
+    __shared__ float4 s_red[2][16][16];        // [sum | sum of squares][point slot][channel group]
+    pnae_pdl_release();
     const int cg = threadIdx.x & 15;           // channels 4*cg .. 4*cg+3
     float wx[4], wy[4], wz[4], bb[4], sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -90,6 +89,7 @@ mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__r
         wx[j] = __ldg(w + 4 * cg + j); wy[j] = __ldg(w + 64 + 4 * cg + j); wz[j] = __ldg(w + 128 + 4 * cg + j);
         bb[j] = __ldg(bias + 4 * cg + j);
     }
+    pnae_pdl_wait();
     for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < npts; p += (long long)gridDim.x * 16) {
         const float x = __ldg(xyz + p * 3), y = __ldg(xyz + p * 3 + 1), z = __ldg(xyz + p * 3 + 2);
         float v[4];
@@ -100,14 +100,19 @@ mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__r
         }
         *reinterpret_cast<float4 *>(out + p * 64 + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        // the 16 threads of a half-warp with the same cg differ in bit 4 of the lane only
-        sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], 16); sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
-        if ((threadIdx.x & 16) == 0) { atomicAdd(&s_stats[0][4 * cg + j], sum[j]); atomicAdd(&s_stats[1][4 * cg + j], sq[j]); }
-    }
+    // the 16 point slots of a channel group meet in shared memory and are added in a fixed order (shared-memory float
+    // atomics are compare-and-swap loops and serialise badly): one global atomic per channel and CTA
+    s_red[0][threadIdx.x >> 4][cg] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+    s_red[1][threadIdx.x >> 4][cg] = make_float4(sq[0], sq[1], sq[2], sq[3]);
     __syncthreads();
-    if (threadIdx.x < 128) atomicAdd(stats + threadIdx.x, s_stats[threadIdx.x >> 6][threadIdx.x & 63]);
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+        const float *r = reinterpret_cast<const float *>(&s_red[which][0][0]) + c;
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) a += r[i * 64];
+        atomicAdd(stats + threadIdx.x, a);
+    }
 }
 
 // Layers 2-4: out[p, c0 + c] = relu(s_prev * in[p, :] + t_prev) . W[:, c0 + c] + bias[c0 + c],  c < 64, c0 = 64 * blockIdx.y
@@ -116,6 +121,17 @@ mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__r
 //   B (8x8, col):  b0 = (k=t, n=g)  b1 = (k=t+4, n=g)
 //   C (16x8):      c0 = (g, 2t)  c1 = (g, 2t+1)  c2 = (g+8, 2t)  c3 = (g+8, 2t+1)
 // With rows of A padded to 68 floats the 32 lanes of an A fragment load hit 32 distinct banks; W is stored in fragment order.
+#ifdef PNAE_MLP_TRACE                  // tuning builds only (tools/mlp_trace.py): SM-clock timestamps of two CTAs' phases
+__device__ long long g_mlp_trace[2][32];
+#define MLP_TRACE(i) do { if (trace_cta >= 0 && threadIdx.x == 0 && (i) < 32) g_mlp_trace[trace_cta][i] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int pnae_debug_mlp_trace(long long *host)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_mlp_trace, sizeof(g_mlp_trace));
+}
+#else
+#define MLP_TRACE(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const BnPrev bn, const float *__restrict__ w,
                  const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ stats)
@@ -129,30 +145,11 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
     float *s_stats = tp + kKin;                                       // [2][kCols]
     const int c0 = blockIdx.y * kCols;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-
-    // W in FRAGMENT ORDER: for k-step ks and n-tile pair np, the four values lane (g, t) needs -- (b0, b1) of n-tile 2 np
-    // and (b0, b1) of n-tile 2 np + 1, b0 = W[8 ks + t][8 nt + g], b1 = W[8 ks + t + 4][8 nt + g] -- are 16 contiguous
-    // bytes at [((ks*4 + np)*32 + lane)*4]: four conflict-free LDS.128 per k-step land every B fragment in the
-    // adjacent register pair the MMA wants (no register moves)
-#pragma unroll 8
-    for (int i = threadIdx.x; i < kKin * kCols; i += kMlpThreads) {
-        const int k = i / kCols, c = i - k * kCols;
-        const float v = __ldg(w + (size_t)k * kout + c0 + c);
-        const unsigned hi = tf32_hi(v);
-        const int ks = k >> 3, kh = (k >> 2) & 1, tt = k & 3, nt = c >> 3, gg = c & 7;
-        // [ks][n-tile pair np = nt / 2][lane][nt & 1][kh]: one LDS.128 = the (b0, b1) register pairs of two n-tiles
-        const int idx = (((ks * 4 + (nt >> 1)) * 32 + gg * 4 + tt) << 2) + ((nt & 1) << 1) + kh;
-        Whi[idx] = hi;
-        Wlo[idx] = tf32_lo(v, hi);
-    }
-    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0 && blockIdx.y == 0, sp[threadIdx.x], tp[threadIdx.x]);
-    if (threadIdx.x < 2 * kCols) s_stats[threadIdx.x] = 0.f;
-    float bcol[8][2], sum[8][2], sq[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) { bcol[nt][j] = __ldg(bias + c0 + nt * 8 + 2 * t + j); sum[nt][j] = 0.f; sq[nt][j] = 0.f; }
-    __syncthreads();
+#ifdef PNAE_MLP_TRACE
+    const int trace_cta = blockIdx.y == 0 ? (blockIdx.x == 0 ? 0 : blockIdx.x == 200 ? 1 : -1) : -1;
+    int tr = 4;
+#endif
+    MLP_TRACE(0);
 
     // Input tiles are double-buffered: the NEXT tile's raw rows arrive by cp.async while this one is multiplied, and the
     // previous layer's BatchNorm + ReLU is applied when a fragment is read (rows past the end repeat the last row; the
@@ -171,23 +168,66 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // tiles are handed out dynamically (one atomic per tile on the counter word behind the statistics): with 1024
-    // tiles on 148 SMs a static split leaves a third of the CTAs one tile short and their SMs idle at the end
+    // The first tile of a CTA is its own index and is requested before anything else, so it lands while the weights are
+    // staged; later tiles are handed out dynamically (one atomic per tile on the counter word behind the statistics:
+    // with 1024 tiles on 148 SMs a static split leaves a third of the CTAs one tile short and their SMs idle at the
+    // end).  The ticket for the tile after next is drawn while this tile is multiplied -- thread 0 keeps it in a register
+    // and publishes it at the barrier that ends the multiply -- so the atomic's round trip is never waited for.
     unsigned *counter = reinterpret_cast<unsigned *>(stats + 2 * (size_t)kout) + blockIdx.y;
     __shared__ long long s_next;
-    auto fetch = [&]() -> long long {
-        if (threadIdx.x == 0) s_next = (long long)atomicAdd(counter, 1u);
-        __syncthreads();
-        const long long v = s_next;
-        __syncthreads();
-        return v;
-    };
-    int buf = 0;
-    long long tile = fetch();
+    long long tile = blockIdx.x;
+    unsigned ticket = 0;
+    pnae_pdl_release();
+
+    // W in FRAGMENT ORDER: for k-step ks and n-tile pair np, the four values lane (g, t) needs -- (b0, b1) of n-tile 2 np
+    // and (b0, b1) of n-tile 2 np + 1, b0 = W[8 ks + t][8 nt + g], b1 = W[8 ks + t + 4][8 nt + g] -- are 16 contiguous
+    // bytes at [((ks*4 + np)*32 + lane)*4]: four conflict-free LDS.128 per k-step land every B fragment in the
+    // adjacent register pair the MMA wants (no register moves).  All of a thread's loads are in flight together.
+    {
+        constexpr int kVec = kKin * kCols / 4 / kMlpThreads;         // float4 loads per thread
+        float4 wv[kVec];
+#pragma unroll
+        for (int j = 0; j < kVec; j++) {
+            const int f = threadIdx.x + j * kMlpThreads, k = f / (kCols / 4), c4 = f - k * (kCols / 4);
+            wv[j] = __ldg(reinterpret_cast<const float4 *>(w + (size_t)k * kout + c0) + c4);
+        }
+#pragma unroll
+        for (int j = 0; j < kVec; j++) {
+            const int f = threadIdx.x + j * kMlpThreads, k = f / (kCols / 4), c4 = f - k * (kCols / 4);
+            const float v4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+            const int ks = k >> 3, kh = (k >> 2) & 1, tt = k & 3;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int c = 4 * c4 + e, nt = c >> 3, gg = c & 7;
+                const unsigned hi = tf32_hi(v4[e]);
+                // [ks][n-tile pair np = nt / 2][lane][nt & 1][kh]: one LDS.128 = the (b0, b1) register pairs of two n-tiles
+                const int idx = (((ks * 4 + (nt >> 1)) * 32 + gg * 4 + tt) << 2) + ((nt & 1) << 1) + kh;
+                Whi[idx] = hi;
+                Wlo[idx] = tf32_lo(v4[e], hi);
+            }
+        }
+    }
+    MLP_TRACE(1);
+    float bcol[8][2], sum[8][2], sq[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { bcol[nt][j] = __ldg(bias + c0 + nt * 8 + 2 * t + j); sum[nt][j] = 0.f; sq[nt][j] = 0.f; }
+    // everything above read only this layer's own parameters and may have run under the previous kernel's tail
+    // (PNAE_OVERLAP_PREVIOUS); the input, its statistics and the tile counter belong to the time after it
+    pnae_pdl_wait();
     if (tile < ntiles) issue(tile, 0);
+    if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0 && blockIdx.y == 0, sp[threadIdx.x], tp[threadIdx.x]);
+    if (threadIdx.x == 0) s_next = (long long)gridDim.x + ticket;
+    __syncthreads();
+    long long nxt = s_next;
+    MLP_TRACE(2);
+
+    int buf = 0;
     for (; tile < ntiles; buf ^= 1) {
         const long long p0 = tile * kTileP;
-        const long long nxt = fetch();
+        if (threadIdx.x == 0 && nxt < ntiles) ticket = atomicAdd(counter, 1u);       // for the tile after `nxt`
         if (nxt < ntiles) {
             issue(nxt, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -195,6 +235,9 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+#ifdef PNAE_MLP_TRACE
+        MLP_TRACE(tr); tr++;
+#endif
 
         // ---- 16 points x 64 channels per warp, K = 64 in 8 steps; 3xTF32: hi*hi + lo*hi + hi*lo
         float acc[8][4];
@@ -233,7 +276,11 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], ahi, bhi[nt]);
         }
+        if (threadIdx.x == 0) s_next = nxt < ntiles ? (long long)gridDim.x + ticket : ntiles;
         __syncthreads();          // every warp is done with this buffer: the next iteration refills it
+#ifdef PNAE_MLP_TRACE
+        MLP_TRACE(tr); tr++;
+#endif
 
         // ---- epilogue: bias, raw output, statistics over the live rows
 #pragma unroll
@@ -251,22 +298,35 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
                 }
             }
         tile = nxt;
+        nxt = s_next;             // (rewritten only after the next iteration's first barrier)
+#ifdef PNAE_MLP_TRACE
+        MLP_TRACE(tr); tr++;
+#endif
     }
-    // lanes with the same t hold the same channels: fold the 8 values of g
+    MLP_TRACE(30);
+    // Statistics of this CTA: every lane parks its 32 partial sums in shared memory (the input buffers are free now; rows
+    // padded to 33 words keep both sides conflict-free) and thread (which, channel) adds the 32 contributions -- 4 warps x
+    // 8 row groups -- of its channel, in a fixed order, and sends one atomic to the global sums.  (Shared-memory float
+    // atomics are compare-and-swap loops: with sixteen lanes per address they took 3 us of a 17 us CTA.)
+    float *red = As;                                                  // [2][kCols][33]
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            float a = sum[nt][j], b = sq[nt][j];
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-            if (g == 0) { atomicAdd(&s_stats[nt * 8 + 2 * t + j], a); atomicAdd(&s_stats[kCols + nt * 8 + 2 * t + j], b); }
+            const int c = nt * 8 + 2 * t + j;
+            red[c * 33 + warp * 8 + g] = sum[nt][j];
+            red[(kCols + c) * 33 + warp * 8 + g] = sq[nt][j];
         }
     __syncthreads();
     if (threadIdx.x < 2 * kCols) {
         const int which = threadIdx.x / kCols, c = threadIdx.x - which * kCols;
-        atomicAdd(stats + (size_t)which * kout + c0 + c, s_stats[threadIdx.x]);
+        const float *r = red + threadIdx.x * 33;
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) a += r[i];
+        atomicAdd(stats + (size_t)which * kout + c0 + c, a);
     }
+    MLP_TRACE(31);
 }
 
 // relu(s * y + t) -> bf16, (npts, k) row-major = the K-major operand tile layout the conv5 kernel's TMA map expects
@@ -274,6 +334,8 @@ __global__ void __launch_bounds__(256)
 mlp_apply_bf16_kernel(long long n4, int k, const float *__restrict__ in, const BnPrev bn, __nv_bfloat16 *__restrict__ out)
 {
     __shared__ float s[256], t[256];
+    pnae_pdl_release();
+    pnae_pdl_wait();
     for (int c = threadIdx.x; c < k; c += blockDim.x) bn_fold_channel(bn, k, c, blockIdx.x == 0, s[c], t[c]);
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -324,6 +386,8 @@ __global__ void conv5_finish_kernel(int b, int c, const float *__restrict__ vmax
                                     float *__restrict__ pooled, float *__restrict__ inv_out, float *__restrict__ mean0_out,
                                     float *__restrict__ ext0_out, float *__restrict__ z_out)
 {
+    pnae_pdl_release();
+    pnae_pdl_wait();
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
     float mean0, var;
@@ -350,15 +414,16 @@ constexpr size_t kLayerSmem = sizeof(float) * (2 * kTileP * kLdA + 2 * kKin * kL
 
 }  // namespace
 
-extern "C" int pnae_mlp_first(long long npts, const float *xyz, const float *w, const float *bias, float *out, float *stats, void *stream)
+extern "C" int pnae_mlp_first(long long npts, const float *xyz, const float *w, const float *bias, float *out, float *stats, int flags,
+                              void *stream)
 {
     PNAE_REQUIRE(npts >= 1 && xyz && w && bias && out && stats, "mlp_first: invalid argument");
     PNAE_REQUIRE(pnae_aligned(out, 16), "mlp_first: out must be 16-byte aligned");
+    PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "mlp_first: unknown flag bits 0x%x", flags);
     cudaStream_t st = (cudaStream_t)stream;
-    PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * 64, st));
+    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * 64, st));
     const int blocks = (int)min((npts + 15) / 16, (long long)pnae_sm_count() * 8);
-    mlp_first_kernel<<<blocks, 256, 0, st>>>(npts, xyz, w, bias, out, stats);
-    PNAE_CUDA_OK(cudaGetLastError());
+    PNAE_CUDA_OK(pnae_launch(mlp_first_kernel, dim3(blocks), dim3(256), 0, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0, npts, xyz, w, bias, out, stats));
     return PNAE_OK;
 }
 
@@ -374,8 +439,9 @@ static BnPrev make_bn(const float *stats, double count, const float *gamma, cons
 extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in,
                               const float *stats_prev, const float *gamma_prev, const float *beta_prev,
                               float *moving_mean_prev, float *moving_var_prev, float eps, float decay, int training,
-                              const float *w, const float *bias, float *out, float *stats, void *stream)
+                              const float *w, const float *bias, float *out, float *stats, int flags, void *stream)
 {
+    PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "mlp_layer: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE(npts >= 1 && in && gamma_prev && beta_prev && moving_mean_prev && moving_var_prev && w && bias && out && stats && (!training || stats_prev),
                  "mlp_layer: invalid argument");
     PNAE_REQUIRE(kin == kKin && kout >= kCols && kout % kCols == 0, "mlp_layer: needs 64 input channels and a multiple of 64 output channels (got %d -> %d)", kin, kout);
@@ -388,12 +454,12 @@ extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in
         PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
         configured[dev] = true;
     }
-    PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / kCols), st));     // statistics + tile counters
+    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / kCols), st));     // statistics + tile counters
     const long long ntiles = (npts + kTileP - 1) / kTileP;
     const int gx = (int)min(ntiles, (long long)pnae_sm_count() * 3);
-    mlp_layer_kernel<<<dim3(gx, kout / kCols), kMlpThreads, kLayerSmem, st>>>(
-        npts, kout, in, make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training), w, bias, out, stats);
-    PNAE_CUDA_OK(cudaGetLastError());
+    PNAE_CUDA_OK(pnae_launch(mlp_layer_kernel, dim3(gx, kout / kCols), dim3(kMlpThreads), kLayerSmem, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+                             npts, kout, in, make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training),
+                             w, bias, out, stats));
     return PNAE_OK;
 }
 
@@ -409,27 +475,30 @@ extern "C" int pnae_bn_fold(int k, const float *stats, double count, const float
 }
 
 extern "C" int pnae_mlp_apply_bf16(long long npts, int k, const float *in, const float *stats, const float *gamma, const float *beta,
-                                   float *moving_mean, float *moving_var, float eps, float decay, int training, void *out_bf16, void *stream)
+                                   float *moving_mean, float *moving_var, float eps, float decay, int training, void *out_bf16, int flags,
+                                   void *stream)
 {
+    PNAE_REQUIRE((flags & ~PNAE_OVERLAP_PREVIOUS) == 0, "mlp_apply_bf16: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE(npts >= 1 && k >= 4 && k % 4 == 0 && k <= 256 && in && gamma && beta && moving_mean && moving_var && out_bf16 && (!training || stats),
                  "mlp_apply_bf16: invalid argument");
     PNAE_REQUIRE(pnae_aligned(in, 16) && pnae_aligned(out_bf16, 8), "mlp_apply_bf16: misaligned buffer");
     const long long n4 = npts * k / 4;
     const int blocks = (int)min((n4 + 255) / 256, (long long)pnae_sm_count() * 16);
-    mlp_apply_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n4, k, in, make_bn(stats, (double)npts, gamma, beta, moving_mean, moving_var, eps, decay, training),
-                                                                     (__nv_bfloat16 *)out_bf16);
-    PNAE_CUDA_OK(cudaGetLastError());
+    PNAE_CUDA_OK(pnae_launch(mlp_apply_bf16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+                             n4, k, in, make_bn(stats, (double)npts, gamma, beta, moving_mean, moving_var, eps, decay, training), (__nv_bfloat16 *)out_bf16));
     return PNAE_OK;
 }
 
 extern "C" int pnae_conv5_finish(int b, int c, double count, const float *vmax, const float *vmin, const float *vsum, const float *vsq,
                                  const float *bias, const float *gamma, const float *beta, float *moving_mean, float *moving_var,
-                                 float eps, float decay, int training, float *pooled, float *inv, float *mean0, float *ext0, float *z, void *stream)
+                                 float eps, float decay, int training, float *pooled, float *inv, float *mean0, float *ext0, float *z, int flags,
+                                 void *stream)
 {
+    PNAE_REQUIRE((flags & ~PNAE_OVERLAP_PREVIOUS) == 0, "conv5_finish: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE(b >= 1 && c >= 1 && count >= 1.0 && vmax && vmin && vsum && vsq && bias && gamma && beta && moving_mean && moving_var && pooled && inv && mean0 && ext0 && z,
                  "conv5_finish: invalid argument");
-    conv5_finish_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b, c, vmax, vmin, vsum, vsq, bias, gamma, beta, moving_mean, moving_var,
-                                                                           (float)(1.0 / count), eps, decay, training, pooled, inv, mean0, ext0, z);
-    PNAE_CUDA_OK(cudaGetLastError());
+    PNAE_CUDA_OK(pnae_launch(conv5_finish_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+                             b, c, vmax, vmin, vsum, vsq, bias, gamma, beta, moving_mean, moving_var, (float)(1.0 / count), eps, decay, training,
+                             pooled, inv, mean0, ext0, z));
     return PNAE_OK;
 }

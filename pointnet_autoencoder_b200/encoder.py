@@ -172,24 +172,32 @@ class _EncoderChain(torch.autograd.Function):
         layers = [tensors[6 * i: 6 * i + 6] for i in range(5)]
         cnt = float(b * n)
 
-        y, st = ops.mlp_first(x.detach(), layers[0][0].detach(), layers[0][1].detach())
+        # Everything that is not one of the seven chain kernels first: conv5's bf16 weights and ONE zeroed arena for the
+        # four layers' statistics.  The seven then follow each other directly and each is enqueued as a programmatic
+        # dependent launch: its set-up (weights to shared memory, barriers, tensor memory) runs under its predecessor's tail.
+        w5, b5, g5, be5, mm5, mv5 = layers[4]
+        wtb = w5.detach().t().contiguous().to(torch.bfloat16)
+        words = [128] + [ops.mlp_stats_words(lay[0].shape[1]) for lay in layers[1:4]]
+        offs = [0]
+        for wd in words:
+            offs.append(offs[-1] + (wd + 3) // 4 * 4)
+        arena = torch.zeros(offs[-1], dtype=torch.float32, device=x.device)
+        y, st = ops.mlp_first(x.detach(), layers[0][0].detach(), layers[0][1].detach(), stats_out=arena[offs[0]: offs[0] + words[0]], overlap=True)
         prev = layers[0]
-        for lay in layers[1:4]:
+        for i, lay in enumerate(layers[1:4], start=1):
             # the previous layer's BatchNorm (+ moving-average update) and ReLU happen inside this layer's kernel
             y, st_next = ops.mlp_layer(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS,
-                                       lay[0].detach(), lay[1].detach())
+                                       lay[0].detach(), lay[1].detach(), stats_out=arena[offs[i]: offs[i] + words[i]], overlap=True)
             st, prev = st_next, lay
-        xb = ops.mlp_apply_bf16(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS).view(b, n, -1)
-        w5, b5, g5, be5, mm5, mv5 = layers[4]
+        xb = ops.mlp_apply_bf16(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS, overlap=True).view(b, n, -1)
         need_arg = any(ctx.needs_input_grad)
-        wtb = w5.detach().t().contiguous().to(torch.bfloat16)
         if need_arg:
-            vmax, vmin, vsum, vsq, arg = ops.encoder_conv_pool(xb, wtb, sign=g5.detach())
+            vmax, vmin, vsum, vsq, arg = ops.encoder_conv_pool(xb, wtb, sign=g5.detach(), overlap=True)
         else:
-            vmax, vmin, vsum, vsq = ops.encoder_conv_pool(xb, wtb)
+            vmax, vmin, vsum, vsq = ops.encoder_conv_pool(xb, wtb, overlap=True)
             arg = None
         pooled, inv, mean0, ext0, z = ops.conv5_finish(vmax, vmin, vsum, vsq, cnt, b5.detach(), g5.detach(), be5.detach(), mm5, mv5,
-                                                       training, decay, BN_EPS)
+                                                       training, decay, BN_EPS, overlap=True)
         cnt5 = cnt
         if need_arg:
             ctx.save_for_backward(x, xb, inv, mean0, ext0, arg, z, *tensors)

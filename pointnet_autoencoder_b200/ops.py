@@ -225,9 +225,23 @@ def match_cost_factors(xyz1, xyz2, factors, with_grad=True):
 # ---------------------------------------------------------------------------
 # encoder: conv5 + max-pool (models/model.py:57-66)
 # ---------------------------------------------------------------------------
-def encoder_conv_pool(x_bf16, wt_bf16, sign=None):
+# flags of the encoder entry points (include/pnae.h)
+STATS_ZEROED = 1
+OVERLAP_PREVIOUS = 2
+
+
+def _overlap_flag(overlap, *pairs):
+    """OVERLAP_PREVIOUS if asked for and none of the (given, used) parameter tensors had to be converted: a conversion
+    is a kernel that writes the parameter immediately before the call, which is what the flag's contract excludes"""
+    if not overlap:
+        return 0
+    return OVERLAP_PREVIOUS if all(a.data_ptr() == b.data_ptr() for a, b in pairs) else 0
+
+
+def encoder_conv_pool(x_bf16, wt_bf16, sign=None, overlap=False):
     """x (B,N,K) bf16, wt (C,K) bf16 -> max, min, sum, sumsq of x @ wt.T over the points, each (B,C) fp32.
-    With `sign` (C,) fp32 also -> arg (B,C) int32: first point attaining the max (sign>=0) / min (sign<0)."""
+    With `sign` (C,) fp32 also -> arg (B,C) int32: first point attaining the max (sign>=0) / min (sign<0).
+    overlap: PNAE_OVERLAP_PREVIOUS -- the kernel enqueued just before this call does not write `wt_bf16`."""
     _dev(x_bf16, "x"); _dev(wt_bf16, "wt")
     _require(x_bf16.dim() == 3 and wt_bf16.dim() == 2 and x_bf16.shape[2] == wt_bf16.shape[1],
              "encoder_conv_pool expects x (batch,#points,k) and wt (c,k)")
@@ -246,25 +260,41 @@ def encoder_conv_pool(x_bf16, wt_bf16, sign=None):
             sign = _f32c(_dev(sign, "sign"))
             arg = torch.empty((b, c), dtype=torch.int32, device=dev)
         _lib.check(lib.pnae_encoder_conv_pool(b, n, k, c, _p(x), _p(wt), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
-                                              _p(sign), _p(arg), _stream(x)))
+                                              _p(sign), _p(arg), _overlap_flag(overlap, (wt_bf16, wt)), _stream(x)))
     return tuple(outs) if arg is None else tuple(outs) + (arg,)
 
 
 # ---------------------------------------------------------------------------
 # encoder layers 1-4 (csrc/shared_mlp.cu)
 # ---------------------------------------------------------------------------
-def mlp_first(xyz, w, bias):
-    """layer 1: xyz (B,N,3) fp32, w (3,64), bias (64,) -> raw output (B*N,64) fp32, stats (2,64) = per-channel sum / sum of squares"""
+def _stats_arg(stats_out, words, dev):
+    """the statistics buffer of a layer call: a fresh one (the call zeroes it) or the caller's zeroed view (STATS_ZEROED)"""
+    if stats_out is None:
+        return torch.empty((words,), dtype=torch.float32, device=dev), 0
+    _require(stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == words and stats_out.device == dev,
+             "stats_out must be a contiguous zeroed fp32 tensor of %d words on the input's device" % words)
+    return stats_out, STATS_ZEROED
+
+
+def mlp_stats_words(kout):
+    """words of the statistics buffer of an mlp_layer call with kout output channels: sums, sums of squares, tile counters"""
+    return 2 * kout + kout // 64
+
+
+def mlp_first(xyz, w, bias, stats_out=None, overlap=False):
+    """layer 1: xyz (B,N,3) fp32, w (3,64), bias (64,) -> raw output (B*N,64) fp32, stats (2,64) = per-channel sum / sum of squares.
+    stats_out: a zeroed (128,) view to accumulate into (saves the call's own memset); overlap: PNAE_OVERLAP_PREVIOUS."""
     _dev(xyz, "xyz")
     _require(xyz.dim() == 3 and xyz.shape[2] == 3 and tuple(w.shape) == (3, 64) and tuple(bias.shape) == (64,), "mlp_first expects xyz (batch,#points,3), w (3,64), bias (64,)")
+    w0, bias0 = w, bias
     x = _f32c(xyz); w = _f32c(_dev(w, "w")); bias = _f32c(_dev(bias, "bias"))
     npts = x.shape[0] * x.shape[1]
     lib = _lib.load()
     with torch.cuda.device(x.device):
         out = torch.empty((npts, 64), dtype=torch.float32, device=x.device)
-        stats = torch.empty((2, 64), dtype=torch.float32, device=x.device)
-        _lib.check(lib.pnae_mlp_first(npts, _p(x), _p(w), _p(bias), _p(out), _p(stats), _stream(x)))
-    return out, stats
+        stats, zf = _stats_arg(stats_out, 128, x.device)
+        _lib.check(lib.pnae_mlp_first(npts, _p(x), _p(w), _p(bias), _p(out), _p(stats), zf | _overlap_flag(overlap, (w0, w), (bias0, bias)), _stream(x)))
+    return out, stats.view(2, 64)
 
 
 def _bn_args(k, stats, gamma, beta, moving_mean, moving_var, training):
@@ -276,21 +306,25 @@ def _bn_args(k, stats, gamma, beta, moving_mean, moving_var, training):
     return _f32c(_dev(gamma, "gamma")), _f32c(_dev(beta, "beta"))
 
 
-def mlp_layer(y_prev, stats_prev, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, training, decay, eps, w, bias):
+def mlp_layer(y_prev, stats_prev, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, training, decay, eps, w, bias,
+              stats_out=None, overlap=False):
     """layers 2-4: relu(BatchNorm_prev(y_prev)) @ w + bias -> raw output (T,kout) fp32, stats (2,kout).
     BatchNorm_prev uses batch statistics formed from stats_prev (training; the moving statistics are updated in place,
-    TF convention) or the moving statistics (inference)."""
+    TF convention) or the moving statistics (inference).
+    stats_out: a zeroed (mlp_stats_words(kout),) view to accumulate into; overlap: PNAE_OVERLAP_PREVIOUS."""
     _dev(y_prev, "y_prev")
     kin, kout = w.shape
     _require(y_prev.dim() == 2 and y_prev.shape[1] == kin and tuple(bias.shape) == (kout,), "mlp_layer expects y_prev (points,kin), w (kin,kout), bias (kout,)")
     g, b = _bn_args(kin, stats_prev, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, training)
+    w0, bias0 = w, bias
     y = _f32c(y_prev); w = _f32c(_dev(w, "w")); bias = _f32c(_dev(bias, "bias"))
     lib = _lib.load()
     with torch.cuda.device(y.device):
         out = torch.empty((y.shape[0], kout), dtype=torch.float32, device=y.device)
-        buf = torch.empty((2 * kout + kout // 64,), dtype=torch.float32, device=y.device)      # statistics + the kernel's tile counters
+        buf, zf = _stats_arg(stats_out, 2 * kout + kout // 64, y.device)                       # statistics + the kernel's tile counters
         _lib.check(lib.pnae_mlp_layer(y.shape[0], kin, kout, _p(y), _p(stats_prev), _p(g), _p(b), _p(moving_mean_prev), _p(moving_var_prev),
-                                      float(eps), float(decay), int(bool(training)), _p(w), _p(bias), _p(out), _p(buf), _stream(y)))
+                                      float(eps), float(decay), int(bool(training)), _p(w), _p(bias), _p(out), _p(buf),
+                                      zf | _overlap_flag(overlap, (w0, w), (bias0, bias)), _stream(y)))
     return out, buf[: 2 * kout].view(2, kout)
 
 
@@ -308,7 +342,7 @@ def bn_fold(stats, count, gamma, beta, moving_mean, moving_var, training, decay,
     return s, t
 
 
-def mlp_apply_bf16(y, stats, gamma, beta, moving_mean, moving_var, training, decay, eps):
+def mlp_apply_bf16(y, stats, gamma, beta, moving_mean, moving_var, training, decay, eps, overlap=False):
     """relu(BatchNorm(y)) -> bf16 (T,k): the K-major operand of encoder_conv_pool (BatchNorm given as in mlp_layer)"""
     _dev(y, "y")
     k = y.shape[1]
@@ -319,11 +353,11 @@ def mlp_apply_bf16(y, stats, gamma, beta, moving_mean, moving_var, training, dec
     with torch.cuda.device(y.device):
         out = torch.empty((y.shape[0], k), dtype=torch.bfloat16, device=y.device)
         _lib.check(lib.pnae_mlp_apply_bf16(y.shape[0], k, _p(y), _p(stats), _p(g), _p(b), _p(moving_mean), _p(moving_var),
-                                           float(eps), float(decay), int(bool(training)), _p(out), _stream(y)))
+                                           float(eps), float(decay), int(bool(training)), _p(out), OVERLAP_PREVIOUS if overlap else 0, _stream(y)))
     return out
 
 
-def conv5_finish(vmax, vmin, vsum, vsq, count, bias, gamma, beta, moving_mean, moving_var, training, decay, eps):
+def conv5_finish(vmax, vmin, vsum, vsq, count, bias, gamma, beta, moving_mean, moving_var, training, decay, eps, overlap=False):
     """conv5's bias + BatchNorm + ReLU + max-pool finish on (B,C) in one launch -> pooled, inv (C), mean0 (C), ext0 (B,C), z (B,C)"""
     b, c = vmax.shape
     g, be = _bn_args(c, None, gamma, beta, moving_mean, moving_var, False)
@@ -336,5 +370,5 @@ def conv5_finish(vmax, vmin, vsum, vsq, count, bias, gamma, beta, moving_mean, m
         ext0 = torch.empty((b, c), **f); z = torch.empty((b, c), **f)
         _lib.check(lib.pnae_conv5_finish(b, c, float(count), _p(_f32c(vmax)), _p(_f32c(vmin)), _p(_f32c(vsum)), _p(_f32c(vsq)), _p(bias), _p(g), _p(be),
                                          _p(moving_mean), _p(moving_var), float(eps), float(decay), int(bool(training)),
-                                         _p(pooled), _p(inv), _p(mean0), _p(ext0), _p(z), _stream(vmax)))
+                                         _p(pooled), _p(inv), _p(mean0), _p(ext0), _p(z), OVERLAP_PREVIOUS if overlap else 0, _stream(vmax)))
     return pooled, inv, mean0, ext0, z

@@ -16,8 +16,12 @@ def scaled_err(a, ref):
     return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
 
 
+# the SMs split the (channel block, element, point tile) stream evenly, so these shapes exercise: whole elements per SM,
+# elements cut in two (32, 2048), in many one-tile parts (1, 4096), ranges that cross a channel-block boundary (40, 512),
+# ragged last tiles, and fewer tiles than SMs
 @pytest.mark.parametrize("b,n,k,c", [(2, 256, 128, 1024), (3, 2048, 128, 1024), (2, 300, 128, 256), (1, 1000, 64, 128),
-                                     (4, 37, 128, 128)])
+                                     (4, 37, 128, 128), (32, 2048, 128, 1024), (1, 4096, 128, 1024), (5, 2125, 128, 1024),
+                                     (40, 512, 64, 256), (7, 3000, 128, 384)])
 def test_conv_pool_stats_vs_torch(b, n, k, c):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(b, n, k, device="cuda", generator=g)
@@ -31,6 +35,11 @@ def test_conv_pool_stats_vs_torch(b, n, k, c):
     assert scaled_err(vsq, (y * y).sum(1)) < 1e-4
     y32 = x @ w                                      # the un-rounded fp32 layer: bf16 operand rounding only
     assert scaled_err(vmax, y32.amax(1)) < 2e-2
+    # the merge of an element's parts is in point order whichever SM finishes last: bitwise repeatable, and the tickets
+    # in the cached workspace are left ready for the next call
+    again = ops.encoder_conv_pool(xb, wb.t().contiguous())
+    for a, r in zip(again, (vmax, vmin, vsum, vsq)):
+        assert torch.equal(a, r)
 
 
 @pytest.mark.parametrize("training", [True, False])
@@ -53,9 +62,9 @@ def test_encoder_fused_matches_unfused(training):
         assert scaled_err(enc.conv5.moving_var, ref.conv5.moving_var) < 2e-2
 
 
-def test_conv_pool_argext():
+@pytest.mark.parametrize("b,n,k,c", [(3, 700, 128, 256), (8, 2300, 128, 1024), (1, 4096, 128, 1024)])
+def test_conv_pool_argext(b, n, k, c):
     g = torch.Generator(device="cuda").manual_seed(2)
-    b, n, k, c = 3, 700, 128, 256
     x = torch.randn(b, n, k, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(k, c, device="cuda", generator=g) / k ** 0.5).to(torch.bfloat16)
     sign = torch.randn(c, device="cuda", generator=g)

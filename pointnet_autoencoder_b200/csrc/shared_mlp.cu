@@ -376,37 +376,83 @@ __global__ void bn_fold_kernel(int k, const float *__restrict__ stats, float inv
 }
 
 // conv5's BatchNorm + ReLU + max-pool finish on (B, C): from the tcgen05 kernel's per-(element, channel) max / min / sum /
-// sum of squares of y0 = x @ w (no bias) to the pooled feature, in one launch.  One thread per channel.
+// sum of squares of y0 = x @ w (no bias) to the pooled feature, in one launch.
 //   pooled = relu((ext0 - mean0) * s + beta),  ext0 = max where gamma >= 0 else min,  s = gamma / sqrt(var + eps)
 // Also leaves what the backward needs: inv (C), mean0 (C), ext0 (B,C), z (B,C).
-__global__ void conv5_finish_kernel(int b, int c, const float *__restrict__ vmax, const float *__restrict__ vmin,
-                                    const float *__restrict__ vsum, const float *__restrict__ vsq, const float *__restrict__ bias,
-                                    const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ moving_mean,
-                                    float *__restrict__ moving_var, float inv_count, float eps, float decay, int training,
-                                    float *__restrict__ pooled, float *__restrict__ inv_out, float *__restrict__ mean0_out,
-                                    float *__restrict__ ext0_out, float *__restrict__ z_out)
+// This is the last kernel of the encoder chain, so its latency is all exposed: a CTA owns 32 channels and spreads the
+// batch over 8 thread rows, every load a thread needs (sums for the statistics, extrema for the output) is issued before
+// the first use, and the 8 partial sums of a channel meet in shared memory in a fixed order -- two dependent memory
+// round trips in all (one thread per channel walking the batch took 13 us).
+constexpr int kFinRows = 8, kFinPer = 8;      // thread rows per CTA, batch elements per thread held in registers at once
+__global__ void __launch_bounds__(32 * kFinRows)
+conv5_finish_kernel(int b, int c, const float *__restrict__ vmax, const float *__restrict__ vmin,
+                    const float *__restrict__ vsum, const float *__restrict__ vsq, const float *__restrict__ bias,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ moving_mean,
+                    float *__restrict__ moving_var, float inv_count, float eps, float decay, int training,
+                    float *__restrict__ pooled, float *__restrict__ inv_out, float *__restrict__ mean0_out,
+                    float *__restrict__ ext0_out, float *__restrict__ z_out)
 {
+    __shared__ float s_sum[kFinRows][32], s_sq[kFinRows][32], s_mean[32], s_scale[32];
     pnae_pdl_release();
     pnae_pdl_wait();
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    float mean0, var;
-    if (training) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < b; i++) { s1 += vsum[(size_t)i * c + ch]; s2 += vsq[(size_t)i * c + ch]; }
-        mean0 = s1 * inv_count;
-        var = fmaxf(fmaf(-mean0, mean0, s2 * inv_count), 0.f);
-        moving_mean[ch] = fmaf(decay, moving_mean[ch], (1.f - decay) * (mean0 + bias[ch]));
-        moving_var[ch] = fmaf(decay, moving_var[ch], (1.f - decay) * var);
-    } else {
-        mean0 = moving_mean[ch] - bias[ch]; var = moving_var[ch];
-    }
-    const float inv = 1.0f / sqrtf(var + eps), g = gamma[ch], s = g * inv, be = beta[ch];
-    inv_out[ch] = inv; mean0_out[ch] = mean0;
-    for (int i = 0; i < b; i++) {
-        const float e0 = g >= 0.f ? vmax[(size_t)i * c + ch] : vmin[(size_t)i * c + ch];
-        const float z = fmaf(e0 - mean0, s, be);
-        ext0_out[(size_t)i * c + ch] = e0; z_out[(size_t)i * c + ch] = z; pooled[(size_t)i * c + ch] = fmaxf(z, 0.f);
+    const int cx = threadIdx.x & 31, row = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + cx;
+    const bool live = ch < c;
+    const float g = live ? gamma[ch] : 0.f, be = live ? beta[ch] : 0.f;
+    float mean0 = 0.f, var = 1.f;
+    if (!training && live) { mean0 = moving_mean[ch] - bias[ch]; var = moving_var[ch]; }
+    for (int i0 = 0; i0 < b; i0 += kFinRows * kFinPer) {                      // (one pass for b <= 64)
+        float e0[kFinPer], a1[kFinPer], a2[kFinPer];
+#pragma unroll
+        for (int j = 0; j < kFinPer; j++) {
+            const int i = i0 + row + kFinRows * j;
+            const bool ok = live && i < b;
+            const size_t o = (size_t)i * c + ch;
+            e0[j] = ok ? (g >= 0.f ? vmax[o] : vmin[o]) : 0.f;
+            a1[j] = (ok && training) ? vsum[o] : 0.f;
+            a2[j] = (ok && training) ? vsq[o] : 0.f;
+        }
+        if (training) {
+            // statistics over the WHOLE batch are needed before any output: with b > 64 this first pass only gathers
+            // them (the loop below re-reads the sums of the other passes)
+            if (i0 == 0) {
+                float p1 = 0.f, p2 = 0.f;
+                for (int ib = 0; ib < b; ib += kFinRows * kFinPer) {
+#pragma unroll
+                    for (int j = 0; j < kFinPer; j++) {
+                        const int i = ib + row + kFinRows * j;
+                        if (ib == 0) { p1 += a1[j]; p2 += a2[j]; }
+                        else if (live && i < b) { p1 += vsum[(size_t)i * c + ch]; p2 += vsq[(size_t)i * c + ch]; }
+                    }
+                }
+                s_sum[row][cx] = p1; s_sq[row][cx] = p2;
+                __syncthreads();
+                if (row == 0) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < kFinRows; r++) { s1 += s_sum[r][cx]; s2 += s_sq[r][cx]; }
+                    const float m = s1 * inv_count, v = fmaxf(fmaf(-m, m, s2 * inv_count), 0.f);
+                    s_mean[cx] = m; s_scale[cx] = v;
+                    if (live) {
+                        moving_mean[ch] = fmaf(decay, moving_mean[ch], (1.f - decay) * (m + bias[ch]));
+                        moving_var[ch] = fmaf(decay, moving_var[ch], (1.f - decay) * v);
+                    }
+                }
+                __syncthreads();
+                mean0 = s_mean[cx]; var = s_scale[cx];
+            }
+        }
+        const float inv = 1.0f / sqrtf(var + eps), s = g * inv;
+        if (i0 == 0 && row == 0 && live) { inv_out[ch] = inv; mean0_out[ch] = mean0; }
+#pragma unroll
+        for (int j = 0; j < kFinPer; j++) {
+            const int i = i0 + row + kFinRows * j;
+            if (live && i < b) {
+                const size_t o = (size_t)i * c + ch;
+                const float z = fmaf(e0[j] - mean0, s, be);
+                ext0_out[o] = e0[j]; z_out[o] = z; pooled[o] = fmaxf(z, 0.f);
+            }
+        }
     }
 }
 
@@ -497,7 +543,7 @@ extern "C" int pnae_conv5_finish(int b, int c, double count, const float *vmax, 
     PNAE_REQUIRE((flags & ~PNAE_OVERLAP_PREVIOUS) == 0, "conv5_finish: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE(b >= 1 && c >= 1 && count >= 1.0 && vmax && vmin && vsum && vsq && bias && gamma && beta && moving_mean && moving_var && pooled && inv && mean0 && ext0 && z,
                  "conv5_finish: invalid argument");
-    PNAE_CUDA_OK(pnae_launch(conv5_finish_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
+    PNAE_CUDA_OK(pnae_launch(conv5_finish_kernel, dim3((c + 31) / 32), dim3(32 * kFinRows), 0, (cudaStream_t)stream, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
                              b, c, vmax, vmin, vsum, vsq, bias, gamma, beta, moving_mean, moving_var, (float)(1.0 / count), eps, decay, training,
                              pooled, inv, mean0, ext0, z));
     return PNAE_OK;

@@ -167,7 +167,9 @@ class _EncoderChain(torch.autograd.Function):
     autograd (they are 11 % of the FLOPs, and only their forward is on the measured path)."""
 
     @staticmethod
-    def forward(ctx, x, training, decay, *tensors):
+    def forward(ctx, x, training, decay, grad_mode, *tensors):
+        # grad_mode: torch.is_grad_enabled() at the call (inside forward() it is always off, and needs_input_grad does not
+        # tell): without a backward to come the cheaper kernel variant that does not track the arg-extremum is enough
         b, n, _ = x.shape
         layers = [tensors[6 * i: 6 * i + 6] for i in range(5)]
         cnt = float(b * n)
@@ -190,7 +192,7 @@ class _EncoderChain(torch.autograd.Function):
                                        lay[0].detach(), lay[1].detach(), stats_out=arena[offs[i]: offs[i] + words[i]], overlap=True)
             st, prev = st_next, lay
         xb = ops.mlp_apply_bf16(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS, overlap=True).view(b, n, -1)
-        need_arg = any(ctx.needs_input_grad)
+        need_arg = bool(grad_mode) and any(ctx.needs_input_grad)
         if need_arg:
             vmax, vmin, vsum, vsq, arg = ops.encoder_conv_pool(xb, wtb, sign=g5.detach(), overlap=True)
         else:
@@ -222,7 +224,7 @@ class _EncoderChain(torch.autograd.Function):
                 net = F.relu(yy)
             wanted = [p_ for lay in params for p_ in lay] + ([xin] if ctx.needs_input_grad[0] else [])
             grads = torch.autograd.grad(net, wanted, grad_outputs=dx4.reshape(-1, net.shape[1]), allow_unused=True)
-        out = [grads[-1] if ctx.needs_input_grad[0] else None, None, None]
+        out = [grads[-1] if ctx.needs_input_grad[0] else None, None, None, None]
         for i in range(4):
             out += list(grads[4 * i: 4 * i + 4]) + [None, None]
         out += [dw5, db5, dg5, dbe5, None, None]
@@ -268,7 +270,7 @@ class PointNetEncoder(nn.Module):
             flat = []
             for layer in list(self.layers) + [self.conv5]:
                 flat += [layer.weight, layer.bias, layer.gamma, layer.beta, layer.moving_mean, layer.moving_var]
-            return _EncoderChain.apply(point_cloud, self.training, bn_decay, *flat)
+            return _EncoderChain.apply(point_cloud, self.training, bn_decay, torch.is_grad_enabled(), *flat)
         net = point_cloud
         for layer in self.layers:
             net = layer(net, bn_decay)

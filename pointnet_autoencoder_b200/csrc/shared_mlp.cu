@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include "pnae_common.cuh"
+#include "pnae_tc.cuh"
 
 namespace {
 
@@ -329,6 +330,216 @@ mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const B
     MLP_TRACE(31);
 }
 
+// Layers 2-4 on the fifth-generation tensor cores (tcgen05, kind::tf32, 3xTF32):
+//   D[channel, point] = W^T[channel, :] . a[point, :],   a = relu(s_prev * in + t_prev)
+// as  Whi.ahi + Wlo.ahi + Whi.alo  (hi = the value cut to TF32's 10 mantissa bits, lo = the remainder: fp32 accuracy,
+// see tf32_hi / tf32_lo), 3 x 8 UMMAs of 128 x 256 x 8 per 256-point tile.  Channels are the M (TMEM lane) dimension:
+// an epilogue thread owns one channel, so the statistics are private register sums and a warp's store of one point is
+// 32 consecutive channels = one 128-byte segment of the row-major output.
+//   warp 0      MMA issuer (+ TMEM allocation)
+//   warps 1-8   producers: raw rows from global -> BatchNorm + ReLU -> hi / lo split -> the two 128B-swizzled K-major
+//               operand tiles in shared memory (the layout a TMA load with SWIZZLE_128B would have produced); the
+//               global loads of the NEXT tile are in registers while the tensor cores work on this one
+//   warps 9-12  epilogue: TMEM -> registers -> bias -> global, sum and sum of squares per channel
+// One operand stage (2 x 64 KB for 256 points) next to the resident weights (2 x 32 KB); accumulators double-buffered in
+// TMEM, so the epilogue's stores overlap the next tile's MMAs.  Weights narrower than 128 channels are zero-padded.
+constexpr int kTcPoints = 256;                 // points per tile (UMMA N)
+constexpr int kTcM = 128;                      // channel rows of the weight operand (UMMA M)
+constexpr int kTcProducerWarps = 8, kTcEpiWarps = 4;
+constexpr int kTcThreads = 32 * (1 + kTcProducerWarps + kTcEpiWarps);
+constexpr uint32_t kTcWBytes = 2 * kTcM * 128;         // one weight operand (two 32-element k boxes)
+constexpr uint32_t kTcABytes = 2 * kTcPoints * 128;    // one activation operand
+constexpr size_t kTcSmem = 1024 + 2 * kTcWBytes + 2 * kTcABytes + 256 + 2 * kKin * sizeof(float);
+
+// byte offset of element (row, k) in a K-major SWIZZLE_128B operand of `rows` rows and 64 fp32 columns: two boxes of
+// 32 columns; inside a box a row is 128 bytes and its 16-byte chunks are XOR-ed with the row's position in its group of 8
+__device__ __forceinline__ uint32_t tc_offset(int rows, int row, int k)
+{
+    return (uint32_t)((k >> 5) * rows * 128 + row * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4) + (k & 3) * 4);
+}
+
+template <int KOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev bn, const float *__restrict__ w,
+                    const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ stats)
+{
+#ifdef PNAE_MLP_TRACE
+    const int trace_cta = blockIdx.x == 0 ? 0 : blockIdx.x == 100 ? 1 : -1;
+#define TC_TRACE(i) do { if (trace_cta >= 0 && (i) < 32) g_mlp_trace[trace_cta][i] = clock64(); } while (0)
+#else
+#define TC_TRACE(i) do { } while (0)
+#endif
+    if (threadIdx.x == 0) TC_TRACE(0);
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *Whi = smem, *Wlo = Whi + kTcWBytes, *Ahi = Wlo + kTcWBytes, *Alo = Ahi + kTcABytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Alo + kTcABytes);
+    uint64_t *a_full = bars, *a_empty = bars + 1, *t_full = bars + 2, *t_empty = bars + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    float *sp = reinterpret_cast<float *>(bars) + 64, *tp = sp + kKin;        // folded BatchNorm of the previous layer
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
+    constexpr int kout = KOUT;
+
+    pnae_pdl_release();
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, kTcProducerWarps); mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTcEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // W^T, hi and lo, zero rows past kout.  An item is one 16-byte chunk = 4 consecutive k of one channel; consecutive
+    // threads take consecutive channels, so the four global reads are coalesced and the two 16-byte shared stores of a
+    // quarter warp fall into eight different bank groups (the swizzle XORs the chunk with the row).
+    for (int i = threadIdx.x; i < (kKin / 4) * kTcM; i += kTcThreads) {
+        const int k4 = i / kTcM, c = i - k4 * kTcM;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = c < kout ? __ldg(w + (size_t)(4 * k4 + e) * kout + c) : 0.f;
+        uint4 hi, lo;
+        hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
+        lo.x = tf32_lo(v[0], hi.x); lo.y = tf32_lo(v[1], hi.y); lo.z = tf32_lo(v[2], hi.z); lo.w = tf32_lo(v[3], hi.w);
+        const uint32_t off = tc_offset(kTcM, c, 4 * k4);
+        *reinterpret_cast<uint4 *>(Whi + off) = hi;
+        *reinterpret_cast<uint4 *>(Wlo + off) = lo;
+    }
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) TC_TRACE(1);
+    // everything above read only this layer's own parameters and may have run under the previous kernel's tail
+    // (PNAE_OVERLAP_PREVIOUS); the input and its statistics belong to the time after it
+    pnae_pdl_wait();
+    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0, sp[threadIdx.x], tp[threadIdx.x]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(2);
+
+    if (warp == 0) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(kTcM, kTcPoints);
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                const int buf = it & 1;
+                mbar_wait(a_full, it & 1);
+                if (it >= 2) mbar_wait(t_empty + buf, ((it >> 1) - 1) & 1);      // the epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // small terms first
+                const unsigned char *wa[3] = {Wlo, Whi, Whi};
+                const unsigned char *ab[3] = {Ahi, Alo, Ahi};
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++)
+#pragma unroll
+                    for (int ks = 0; ks < kKin / 8; ks++) {
+                        const int kb = ks >> 2, kin = ks & 3;                      // 4 UMMA_K=8 steps per 128-byte row
+                        const uint64_t ad = umma_desc_sw128(smem_u32(wa[pr] + (size_t)kb * kTcM * 128) + kin * 32);
+                        const uint64_t bd = umma_desc_sw128(smem_u32(ab[pr] + (size_t)kb * kTcPoints * 128) + kin * 32);
+                        umma_tf32(tmem_base + buf * kTcPoints, ad, bd, idesc, (pr | ks) != 0);
+                    }
+                umma_commit(a_empty);           // the operand stage may be rewritten once these MMAs retire
+                umma_commit(t_full + buf);      // accumulator ready for the epilogue
+                TC_TRACE(5 + 4 * it);
+            }
+        }
+    } else if (warp <= kTcProducerWarps) {
+        // ===== producers: a thread owns one 16-byte column chunk (4 input channels) of rows r0, r0 + 16, ... =====
+        const int pt = threadIdx.x - 32;
+        const int c4 = pt & 15, r0 = pt >> 4;
+        float s4[4], t4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { s4[e] = sp[4 * c4 + e]; t4[e] = tp[4 * c4 + e]; }
+        const uint32_t kbase = (uint32_t)((c4 >> 3) * kTcPoints * 128);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const long long p0 = tile * kTcPoints;
+            float4 v[kTcPoints / 16];
+#pragma unroll
+            for (int j = 0; j < kTcPoints / 16; j++) {
+                const long long row = min(p0 + r0 + 16 * j, npts - 1);         // rows past the end repeat the last row; the epilogue ignores them
+                v[j] = __ldg(reinterpret_cast<const float4 *>(in + row * kKin) + c4);
+            }
+            if (it >= 1) mbar_wait(a_empty, (it - 1) & 1);
+            if (pt == 0) TC_TRACE(3 + 4 * it);
+#pragma unroll
+            for (int j = 0; j < kTcPoints / 16; j++) {
+                const int r = r0 + 16 * j;
+                const float a[4] = {fmaxf(fmaf(v[j].x, s4[0], t4[0]), 0.f), fmaxf(fmaf(v[j].y, s4[1], t4[1]), 0.f),
+                                    fmaxf(fmaf(v[j].z, s4[2], t4[2]), 0.f), fmaxf(fmaf(v[j].w, s4[3], t4[3]), 0.f)};
+                uint4 hi, lo;
+                hi.x = tf32_hi(a[0]); hi.y = tf32_hi(a[1]); hi.z = tf32_hi(a[2]); hi.w = tf32_hi(a[3]);
+                lo.x = tf32_lo(a[0], hi.x); lo.y = tf32_lo(a[1], hi.y); lo.z = tf32_lo(a[2], hi.z); lo.w = tf32_lo(a[3], hi.w);
+                const uint32_t off = kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4 *>(Ahi + off) = hi;
+                *reinterpret_cast<uint4 *>(Alo + off) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+            if (pt == 0) TC_TRACE(4 + 4 * it);
+        }
+    } else {
+        // ===== epilogue: one thread per channel =====
+        const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
+        const int ch = q * 32 + lane;
+        const bool live = ch < kout;                               // (whole warps: kout is a multiple of 32)
+        const float bs = live ? __ldg(bias + ch) : 0.f;
+        float sum = 0.f, sq = 0.f;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int buf = it & 1;
+            const long long p0 = tile * kTcPoints;
+            const int valid = (int)min((long long)kTcPoints, npts - p0);
+            mbar_wait(t_full + buf, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (q * 32 < kout) {                                   // (warp-uniform) this quadrant holds real channels
+#pragma unroll 1
+                for (int part = 0; part < kTcPoints / 64; part++) {        // 64 columns at a time: two TMEM loads in flight
+                    if (part * 64 >= valid) break;
+                    uint32_t r[2][32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTcPoints + part * 64;
+                    tmem_ld32_issue(taddr, r[0]);
+                    tmem_ld32_issue(taddr + 32, r[1]);
+                    tmem_ld_wait();
+                    float *op = out + (p0 + part * 64) * KOUT + ch;           // column j of this part: op[j * KOUT], a constant offset
+                    if (part * 64 + 64 <= valid) {
+#pragma unroll
+                        for (int j = 0; j < 64; j++) {
+                            const float y = __uint_as_float(r[j >> 5][j & 31]) + bs;
+                            op[j * KOUT] = y;
+                            sum += y; sq = fmaf(y, y, sq);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 64; j++)
+                            if (part * 64 + j < valid) {
+                                const float y = __uint_as_float(r[j >> 5][j & 31]) + bs;
+                                op[j * KOUT] = y;
+                                sum += y; sq = fmaf(y, y, sq);
+                            }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + buf);
+            if (threadIdx.x == 32 * (1 + kTcProducerWarps)) TC_TRACE(6 + 4 * it);
+        }
+        if (live) { atomicAdd(stats + ch, sum); atomicAdd(stats + kout + ch, sq); }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+    if (threadIdx.x == 0) TC_TRACE(31);
+}
+
 // relu(s * y + t) -> bf16, (npts, k) row-major = the K-major operand tile layout the conv5 kernel's TMA map expects
 __global__ void __launch_bounds__(256)
 mlp_apply_bf16_kernel(long long n4, int k, const float *__restrict__ in, const BnPrev bn, __nv_bfloat16 *__restrict__ out)
@@ -498,14 +709,24 @@ extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in
     PNAE_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
+        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         configured[dev] = true;
     }
     if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / kCols), st));     // statistics + tile counters
+    const BnPrev bn = make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training);
+    if ((kout == 64 || kout == 128) && getenv("PNAE_MLP_LEGACY") == nullptr) {
+        const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
+        const int gx = (int)min(ntiles, (long long)pnae_sm_count());
+        const bool pdl = (flags & PNAE_OVERLAP_PREVIOUS) != 0;
+        if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
+        else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
+        return PNAE_OK;
+    }
     const long long ntiles = (npts + kTileP - 1) / kTileP;
     const int gx = (int)min(ntiles, (long long)pnae_sm_count() * 3);
     PNAE_CUDA_OK(pnae_launch(mlp_layer_kernel, dim3(gx, kout / kCols), dim3(kMlpThreads), kLayerSmem, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
-                             npts, kout, in, make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training),
-                             w, bias, out, stats));
+                             npts, kout, in, bn, w, bias, out, stats));
     return PNAE_OK;
 }
 

@@ -23,9 +23,9 @@ assert _lib.load().pnae_debug_mlp_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 
 for cta in range(2):
     t0 = buf[cta, 0]
     us = lambda i: (buf[cta, i] - t0) / 1.9e3
-    print("CTA %d: W staged %.2f, prologue done %.2f" % (cta, us(1), us(2)))
-    i = 4
-    while i + 2 < 30 and buf[cta, i]:
-        print("   tile: data ready %.2f  multiplied %.2f  stored %.2f" % (us(i), us(i + 1), us(i + 2)))
-        i += 3
-    print("   loop done %.2f, exit %.2f" % (us(30), us(31)))
+    print("CTA %d: W staged %.2f, set-up done %.2f" % (cta, us(1), us(2)))
+    i = 3
+    while i + 3 < 31 and buf[cta, i]:
+        print("   tile: stage free + rows loaded %.2f  operands written %.2f  MMAs issued %.2f  epilogue done %.2f" % (us(i), us(i + 1), us(i + 2), us(i + 3)))
+        i += 4
+    print("   exit %.2f" % us(31))

@@ -8,16 +8,17 @@
 //
 // Training-mode BatchNorm needs a layer's statistics over ALL points before the next layer may start, so the chain
 // is one kernel per layer, each of which
-//   * reads the previous layer's RAW output y (fp32) once (cp.async, double-buffered tiles) and applies that layer's
-//     folded BatchNorm + ReLU when a fragment is read (a = relu(s*y + t); s, t per channel), so normalised
-//     activations never exist in HBM;
-//   * multiplies by W on the tensor cores (mma.sync m16n8k8 TF32 with the 3xTF32 split a = hi + lo, so the
-//     product keeps fp32 accuracy: the reference computes these layers in fp32) and adds the bias;
+//   * reads the previous layer's RAW output y (fp32) once and applies that layer's folded BatchNorm + ReLU on the way
+//     into shared memory (a = relu(s*y + t); s, t per channel), so normalised activations never exist in HBM;
+//   * multiplies by W on the tensor cores (tcgen05 kind::tf32 with the 3xTF32 split a = hi + lo, so the product keeps
+//     fp32 accuracy: the reference computes these layers in fp32) and adds the bias;
 //   * writes its own raw output once and accumulates the per-channel sum and sum of squares BatchNorm needs in
-//     the epilogue (registers -> shuffles -> shared -> one atomic per channel per CTA).
-// The layers are memory-bound (K <= 64: 16.8 MB in, 16.8 / 33.5 MB out at B*N = 65536), which is why these are
-// plain warp-level MMAs and not a tcgen05 pipeline: the tensor pipe is idle either way.  The last kernel applies
-// layer 4's BatchNorm + ReLU and emits the bf16 K-major operand of the conv5 tcgen05 kernel (encoder.cu) directly.
+//     the epilogue (one register pair per channel, one atomic per channel per CTA).
+// The layers are memory-bound (K <= 64: 16.8 MB in, 16.8 / 33.5 MB out at B*N = 65536).  Round 2 first ran them as
+// warp-level mma.sync m16n8k8 MMAs (22 / 35 us per layer: twelve warps per SM, latency-bound, 3 x 192 MMAs per warp and
+// tile on the legacy path); as a tcgen05 pipeline with producer warps they take 9 - 10 us (mlp_layer_tc_kernel below).
+// The last kernel applies layer 4's BatchNorm + ReLU and emits the bf16 K-major operand of the conv5 tcgen05 kernel
+// (encoder.cu) directly.
 #include <cuda_bf16.h>
 
 #include "pnae_common.cuh"
@@ -25,25 +26,13 @@
 
 namespace {
 
-constexpr int kMlpThreads = 128;     // 4 warps, 16 points (one MMA row tile) each
-constexpr int kTileP = 64;           // points per CTA tile: 1024 tiles at B*N = 65536 balance 148 SMs to 1 %
-constexpr int kCols = 64;            // output channels per CTA (grid.y walks wider layers)
 constexpr int kKin = 64;             // input channels of layers 2-4
-constexpr int kLdA = kKin + 4;       // padded leading dimensions: conflict-free fragment loads (see below)
-constexpr int kLdW = kCols;           // W is kept in fragment order (see the kernel): no padding needed
 
 // 3xTF32 split by TRUNCATION: hi = the top 19 bits (what the tensor core reads of an fp32 register anyway), lo = v - hi
 // (exact).  One LOP3 + one FADD per element; cvt.rna.tf32 expands to ~5 instructions on sm_100 and the 2^-21
 // relative difference is below the dropped lo*lo term.
 __device__ __forceinline__ unsigned tf32_hi(float v) { return __float_as_uint(v) & 0xffffe000u; }
 __device__ __forceinline__ unsigned tf32_lo(float v, unsigned hi) { return __float_as_uint(v - __uint_as_float(hi)); }
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 
 // The previous layer's BatchNorm as the consumer kernels see it: batch statistics from that layer's sums (training) or
 // its moving statistics (inference), folded to scale s = gamma / sqrt(var + eps) and shift t = beta - mean * s.  Every
@@ -91,15 +80,27 @@ mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__r
         bb[j] = __ldg(bias + 4 * cg + j);
     }
     pnae_pdl_wait();
-    for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < npts; p += (long long)gridDim.x * 16) {
-        const float x = __ldg(xyz + p * 3), y = __ldg(xyz + p * 3 + 1), z = __ldg(xyz + p * 3 + 2);
-        float v[4];
+    // four points per thread and pass, their coordinates requested together: one memory round trip per 64 points of a CTA
+    for (long long p0 = (long long)blockIdx.x * 64 + (threadIdx.x >> 4); p0 < npts; p0 += (long long)gridDim.x * 64) {
+        float x[4], y[4], z[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            v[j] = fmaf(z, wz[j], fmaf(y, wy[j], fmaf(x, wx[j], bb[j])));
-            sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]);
+        for (int u = 0; u < 4; u++) {
+            const long long p = min(p0 + 16 * u, npts - 1);
+            x[u] = __ldg(xyz + p * 3); y[u] = __ldg(xyz + p * 3 + 1); z[u] = __ldg(xyz + p * 3 + 2);
         }
-        *reinterpret_cast<float4 *>(out + p * 64 + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long p = p0 + 16 * u;
+            if (p < npts) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[j] = fmaf(z[u], wz[j], fmaf(y[u], wy[j], fmaf(x[u], wx[j], bb[j])));
+                    sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]);
+                }
+                *reinterpret_cast<float4 *>(out + p * 64 + 4 * cg) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
     }
     // the 16 point slots of a channel group meet in shared memory and are added in a fixed order (shared-memory float
     // atomics are compare-and-swap loops and serialise badly): one global atomic per channel and CTA
@@ -116,219 +117,13 @@ mlp_first_kernel(long long npts, const float *__restrict__ xyz, const float *__r
     }
 }
 
-// Layers 2-4: out[p, c0 + c] = relu(s_prev * in[p, :] + t_prev) . W[:, c0 + c] + bias[c0 + c],  c < 64, c0 = 64 * blockIdx.y
-// Persistent CTAs over 128-point tiles.  Fragment layouts of mma.m16n8k8 (g = lane / 4, t = lane % 4):
-//   A (16x8, row): a0 = (g, t)  a1 = (g+8, t)  a2 = (g, t+4)  a3 = (g+8, t+4)
-//   B (8x8, col):  b0 = (k=t, n=g)  b1 = (k=t+4, n=g)
-//   C (16x8):      c0 = (g, 2t)  c1 = (g, 2t+1)  c2 = (g+8, 2t)  c3 = (g+8, 2t+1)
-// With rows of A padded to 68 floats the 32 lanes of an A fragment load hit 32 distinct banks; W is stored in fragment order.
 #ifdef PNAE_MLP_TRACE                  // tuning builds only (tools/mlp_trace.py): SM-clock timestamps of two CTAs' phases
 __device__ long long g_mlp_trace[2][32];
-#define MLP_TRACE(i) do { if (trace_cta >= 0 && threadIdx.x == 0 && (i) < 32) g_mlp_trace[trace_cta][i] = clock64(); } while (0)
 extern "C" __attribute__((visibility("default"))) int pnae_debug_mlp_trace(long long *host)
 {
     return (int)cudaMemcpyFromSymbol(host, g_mlp_trace, sizeof(g_mlp_trace));
 }
-#else
-#define MLP_TRACE(i) do { } while (0)
 #endif
-
-__global__ void __launch_bounds__(kMlpThreads)
-mlp_layer_kernel(long long npts, int kout, const float *__restrict__ in, const BnPrev bn, const float *__restrict__ w,
-                 const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ stats)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *As = reinterpret_cast<float *>(smem_raw);                 // [2][kTileP][kLdA]   raw input tiles (double buffer)
-    unsigned *Whi = reinterpret_cast<unsigned *>(As + 2 * kTileP * kLdA); // [kKin][kLdW]     tf32(W)
-    unsigned *Wlo = Whi + kKin * kLdW;                                // [kKin][kLdW]     tf32(W - hi)
-    float *sp = reinterpret_cast<float *>(Wlo + kKin * kLdW);         // [kKin] s_prev, [kKin] t_prev
-    float *tp = sp + kKin;
-    float *s_stats = tp + kKin;                                       // [2][kCols]
-    const int c0 = blockIdx.y * kCols;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#ifdef PNAE_MLP_TRACE
-    const int trace_cta = blockIdx.y == 0 ? (blockIdx.x == 0 ? 0 : blockIdx.x == 200 ? 1 : -1) : -1;
-    int tr = 4;
-#endif
-    MLP_TRACE(0);
-
-    // Input tiles are double-buffered: the NEXT tile's raw rows arrive by cp.async while this one is multiplied, and the
-    // previous layer's BatchNorm + ReLU is applied when a fragment is read (rows past the end repeat the last row; the
-    // epilogue ignores them).
-    const long long ntiles = (npts + kTileP - 1) / kTileP;
-    // a thread always copies the same 16-byte column slot (q) of rows r0, r0 + 8, ...: one pointer, constant strides
-    const int q = threadIdx.x & 15, r0 = threadIdx.x >> 4;
-    const unsigned as_s = (unsigned)__cvta_generic_to_shared(As) + (unsigned)((r0 * kLdA + 4 * q) * sizeof(float));
-    auto issue = [&](long long tile, int buf) {
-        const long long p0 = tile * kTileP + r0;
-        const unsigned d = as_s + (unsigned)(buf * kTileP * kLdA * sizeof(float));
-#pragma unroll
-        for (int j = 0; j < kTileP / 8; j++) {
-            const long long row = min(p0 + 8 * j, npts - 1);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (unsigned)(8 * j * kLdA * sizeof(float))), "l"(in + row * kKin + 4 * q));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // The first tile of a CTA is its own index and is requested before anything else, so it lands while the weights are
-    // staged; later tiles are handed out dynamically (one atomic per tile on the counter word behind the statistics:
-    // with 1024 tiles on 148 SMs a static split leaves a third of the CTAs one tile short and their SMs idle at the
-    // end).  The ticket for the tile after next is drawn while this tile is multiplied -- thread 0 keeps it in a register
-    // and publishes it at the barrier that ends the multiply -- so the atomic's round trip is never waited for.
-    unsigned *counter = reinterpret_cast<unsigned *>(stats + 2 * (size_t)kout) + blockIdx.y;
-    __shared__ long long s_next;
-    long long tile = blockIdx.x;
-    unsigned ticket = 0;
-    pnae_pdl_release();
-
-    // W in FRAGMENT ORDER: for k-step ks and n-tile pair np, the four values lane (g, t) needs -- (b0, b1) of n-tile 2 np
-    // and (b0, b1) of n-tile 2 np + 1, b0 = W[8 ks + t][8 nt + g], b1 = W[8 ks + t + 4][8 nt + g] -- are 16 contiguous
-    // bytes at [((ks*4 + np)*32 + lane)*4]: four conflict-free LDS.128 per k-step land every B fragment in the
-    // adjacent register pair the MMA wants (no register moves).  All of a thread's loads are in flight together.
-    {
-        constexpr int kVec = kKin * kCols / 4 / kMlpThreads;         // float4 loads per thread
-        float4 wv[kVec];
-#pragma unroll
-        for (int j = 0; j < kVec; j++) {
-            const int f = threadIdx.x + j * kMlpThreads, k = f / (kCols / 4), c4 = f - k * (kCols / 4);
-            wv[j] = __ldg(reinterpret_cast<const float4 *>(w + (size_t)k * kout + c0) + c4);
-        }
-#pragma unroll
-        for (int j = 0; j < kVec; j++) {
-            const int f = threadIdx.x + j * kMlpThreads, k = f / (kCols / 4), c4 = f - k * (kCols / 4);
-            const float v4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
-            const int ks = k >> 3, kh = (k >> 2) & 1, tt = k & 3;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int c = 4 * c4 + e, nt = c >> 3, gg = c & 7;
-                const unsigned hi = tf32_hi(v4[e]);
-                // [ks][n-tile pair np = nt / 2][lane][nt & 1][kh]: one LDS.128 = the (b0, b1) register pairs of two n-tiles
-                const int idx = (((ks * 4 + (nt >> 1)) * 32 + gg * 4 + tt) << 2) + ((nt & 1) << 1) + kh;
-                Whi[idx] = hi;
-                Wlo[idx] = tf32_lo(v4[e], hi);
-            }
-        }
-    }
-    MLP_TRACE(1);
-    float bcol[8][2], sum[8][2], sq[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) { bcol[nt][j] = __ldg(bias + c0 + nt * 8 + 2 * t + j); sum[nt][j] = 0.f; sq[nt][j] = 0.f; }
-    // everything above read only this layer's own parameters and may have run under the previous kernel's tail
-    // (PNAE_OVERLAP_PREVIOUS); the input, its statistics and the tile counter belong to the time after it
-    pnae_pdl_wait();
-    if (tile < ntiles) issue(tile, 0);
-    if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
-    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0 && blockIdx.y == 0, sp[threadIdx.x], tp[threadIdx.x]);
-    if (threadIdx.x == 0) s_next = (long long)gridDim.x + ticket;
-    __syncthreads();
-    long long nxt = s_next;
-    MLP_TRACE(2);
-
-    int buf = 0;
-    for (; tile < ntiles; buf ^= 1) {
-        const long long p0 = tile * kTileP;
-        if (threadIdx.x == 0 && nxt < ntiles) ticket = atomicAdd(counter, 1u);       // for the tile after `nxt`
-        if (nxt < ntiles) {
-            issue(nxt, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-#ifdef PNAE_MLP_TRACE
-        MLP_TRACE(tr); tr++;
-#endif
-
-        // ---- 16 points x 64 channels per warp, K = 64 in 8 steps; 3xTF32: hi*hi + lo*hi + hi*lo
-        float acc[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[nt][j] = 0.f;
-        const float *Aw = As + (size_t)buf * kTileP * kLdA + (warp * 16) * kLdA;
-#pragma unroll
-        for (int ks = 0; ks < kKin / 8; ks++) {
-            const float s0 = sp[ks * 8 + t], t0 = tp[ks * 8 + t], s1 = sp[ks * 8 + t + 4], t1 = tp[ks * 8 + t + 4];
-            unsigned ahi[4], alo[4];
-            {
-                const float *ap = Aw + g * kLdA + ks * 8 + t;
-                const float a[4] = {fmaxf(fmaf(ap[0], s0, t0), 0.f), fmaxf(fmaf(ap[8 * kLdA], s0, t0), 0.f),
-                                    fmaxf(fmaf(ap[4], s1, t1), 0.f), fmaxf(fmaf(ap[8 * kLdA + 4], s1, t1), 0.f)};
-#pragma unroll
-                for (int j = 0; j < 4; j++) { ahi[j] = tf32_hi(a[j]); alo[j] = tf32_lo(a[j], ahi[j]); }
-            }
-            unsigned bhi[8][2], blo[8][2];
-#pragma unroll
-            for (int np = 0; np < 4; np++) {
-                const uint4 h = *reinterpret_cast<const uint4 *>(Whi + (((ks * 4 + np) * 32 + lane) << 2));
-                const uint4 l = *reinterpret_cast<const uint4 *>(Wlo + (((ks * 4 + np) * 32 + lane) << 2));
-                bhi[2 * np][0] = h.x; bhi[2 * np][1] = h.y; bhi[2 * np + 1][0] = h.z; bhi[2 * np + 1][1] = h.w;
-                blo[2 * np][0] = l.x; blo[2 * np][1] = l.y; blo[2 * np + 1][0] = l.z; blo[2 * np + 1][1] = l.w;
-            }
-            // three passes over the 8 accumulators (small terms first): consecutive MMAs are independent, and the
-            // three that feed one accumulator are 8 instructions apart instead of back to back
-#ifndef PNAE_MLP_TF32X1           // (tuning experiment: single-pass TF32, 1e-3 accuracy)
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], alo, bhi[nt]);
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], ahi, blo[nt]);
-#endif
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) mma_tf32(acc[nt], ahi, bhi[nt]);
-        }
-        if (threadIdx.x == 0) s_next = nxt < ntiles ? (long long)gridDim.x + ticket : ntiles;
-        __syncthreads();          // every warp is done with this buffer: the next iteration refills it
-#ifdef PNAE_MLP_TRACE
-        MLP_TRACE(tr); tr++;
-#endif
-
-        // ---- epilogue: bias, raw output, statistics over the live rows
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-                const long long p = p0 + warp * 16 + g + 8 * h;
-                if (p < npts) {
-                    float *op = out + p * kout + c0 + 2 * t;
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const float v0 = acc[nt][2 * h] + bcol[nt][0], v1 = acc[nt][2 * h + 1] + bcol[nt][1];
-                        *reinterpret_cast<float2 *>(op + nt * 8) = make_float2(v0, v1);
-                        sum[nt][0] += v0; sum[nt][1] += v1;
-                        sq[nt][0] = fmaf(v0, v0, sq[nt][0]); sq[nt][1] = fmaf(v1, v1, sq[nt][1]);
-                    }
-                }
-            }
-        tile = nxt;
-        nxt = s_next;             // (rewritten only after the next iteration's first barrier)
-#ifdef PNAE_MLP_TRACE
-        MLP_TRACE(tr); tr++;
-#endif
-    }
-    MLP_TRACE(30);
-    // Statistics of this CTA: every lane parks its 32 partial sums in shared memory (the input buffers are free now; rows
-    // padded to 33 words keep both sides conflict-free) and thread (which, channel) adds the 32 contributions -- 4 warps x
-    // 8 row groups -- of its channel, in a fixed order, and sends one atomic to the global sums.  (Shared-memory float
-    // atomics are compare-and-swap loops: with sixteen lanes per address they took 3 us of a 17 us CTA.)
-    float *red = As;                                                  // [2][kCols][33]
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int c = nt * 8 + 2 * t + j;
-            red[c * 33 + warp * 8 + g] = sum[nt][j];
-            red[(kCols + c) * 33 + warp * 8 + g] = sq[nt][j];
-        }
-    __syncthreads();
-    if (threadIdx.x < 2 * kCols) {
-        const int which = threadIdx.x / kCols, c = threadIdx.x - which * kCols;
-        const float *r = red + threadIdx.x * 33;
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i++) a += r[i];
-        atomicAdd(stats + (size_t)which * kout + c0 + c, a);
-    }
-    MLP_TRACE(31);
-}
 
 // Layers 2-4 on the fifth-generation tensor cores (tcgen05, kind::tf32, 3xTF32):
 //   D[channel, point] = W^T[channel, :] . a[point, :],   a = relu(s_prev * in + t_prev)
@@ -374,8 +169,8 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *Whi = smem, *Wlo = Whi + kTcWBytes, *Ahi = Wlo + kTcWBytes, *Alo = Ahi + kTcABytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(Alo + kTcABytes);
-    uint64_t *a_full = bars, *a_empty = bars + 1, *t_full = bars + 2, *t_empty = bars + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    uint64_t *hi_full = bars, *lo_full = bars + 1, *hi_empty = bars + 2, *lo_empty = bars + 3, *t_full = bars + 4, *t_empty = bars + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
     float *sp = reinterpret_cast<float *>(bars) + 64, *tp = sp + kKin;        // folded BatchNorm of the previous layer
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
@@ -383,7 +178,7 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
 
     pnae_pdl_release();
     if (threadIdx.x == 0) {
-        mbar_init(a_full, kTcProducerWarps); mbar_init(a_empty, 1);
+        mbar_init(hi_full, kTcProducerWarps); mbar_init(lo_full, kTcProducerWarps); mbar_init(hi_empty, 1); mbar_init(lo_empty, 1);
         for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTcEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -425,14 +220,17 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
             int it = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 const int buf = it & 1;
-                mbar_wait(a_full, it & 1);
                 if (it >= 2) mbar_wait(t_empty + buf, ((it >> 1) - 1) & 1);      // the epilogue drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // small terms first
+                // The two products that read a_hi first, a_lo's last: the producers write the next tile's a_hi while the
+                // third product runs and its a_lo while the next tile's first two do, so the tensor pipe never waits for
+                // a whole tile to be staged.
                 const unsigned char *wa[3] = {Wlo, Whi, Whi};
-                const unsigned char *ab[3] = {Ahi, Alo, Ahi};
+                const unsigned char *ab[3] = {Ahi, Ahi, Alo};
 #pragma unroll
-                for (int pr = 0; pr < 3; pr++)
+                for (int pr = 0; pr < 3; pr++) {
+                    if (pr == 0) mbar_wait(hi_full, it & 1);
+                    if (pr == 2) mbar_wait(lo_full, it & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int ks = 0; ks < kKin / 8; ks++) {
                         const int kb = ks >> 2, kin = ks & 3;                      // 4 UMMA_K=8 steps per 128-byte row
@@ -440,7 +238,9 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
                         const uint64_t bd = umma_desc_sw128(smem_u32(ab[pr] + (size_t)kb * kTcPoints * 128) + kin * 32);
                         umma_tf32(tmem_base + buf * kTcPoints, ad, bd, idesc, (pr | ks) != 0);
                     }
-                umma_commit(a_empty);           // the operand stage may be rewritten once these MMAs retire
+                    if (pr == 1) umma_commit(hi_empty);     // a_hi may be rewritten once the first two products retire
+                }
+                umma_commit(lo_empty);          // ... and a_lo once the third does
                 umma_commit(t_full + buf);      // accumulator ready for the epilogue
                 TC_TRACE(5 + 4 * it);
             }
@@ -462,23 +262,36 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
                 const long long row = min(p0 + r0 + 16 * j, npts - 1);         // rows past the end repeat the last row; the epilogue ignores them
                 v[j] = __ldg(reinterpret_cast<const float4 *>(in + row * kKin) + c4);
             }
-            if (it >= 1) mbar_wait(a_empty, (it - 1) & 1);
+            // BatchNorm + ReLU in place, then the two operand tiles one after the other, each behind its own barriers
+#pragma unroll
+            for (int j = 0; j < kTcPoints / 16; j++) {
+                v[j].x = fmaxf(fmaf(v[j].x, s4[0], t4[0]), 0.f); v[j].y = fmaxf(fmaf(v[j].y, s4[1], t4[1]), 0.f);
+                v[j].z = fmaxf(fmaf(v[j].z, s4[2], t4[2]), 0.f); v[j].w = fmaxf(fmaf(v[j].w, s4[3], t4[3]), 0.f);
+            }
+            if (it >= 1) mbar_wait(hi_empty, (it - 1) & 1);
             if (pt == 0) TC_TRACE(3 + 4 * it);
 #pragma unroll
             for (int j = 0; j < kTcPoints / 16; j++) {
                 const int r = r0 + 16 * j;
-                const float a[4] = {fmaxf(fmaf(v[j].x, s4[0], t4[0]), 0.f), fmaxf(fmaf(v[j].y, s4[1], t4[1]), 0.f),
-                                    fmaxf(fmaf(v[j].z, s4[2], t4[2]), 0.f), fmaxf(fmaf(v[j].w, s4[3], t4[3]), 0.f)};
-                uint4 hi, lo;
-                hi.x = tf32_hi(a[0]); hi.y = tf32_hi(a[1]); hi.z = tf32_hi(a[2]); hi.w = tf32_hi(a[3]);
-                lo.x = tf32_lo(a[0], hi.x); lo.y = tf32_lo(a[1], hi.y); lo.z = tf32_lo(a[2], hi.z); lo.w = tf32_lo(a[3], hi.w);
-                const uint32_t off = kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4));
-                *reinterpret_cast<uint4 *>(Ahi + off) = hi;
-                *reinterpret_cast<uint4 *>(Alo + off) = lo;
+                uint4 hi;
+                hi.x = tf32_hi(v[j].x); hi.y = tf32_hi(v[j].y); hi.z = tf32_hi(v[j].z); hi.w = tf32_hi(v[j].w);
+                *reinterpret_cast<uint4 *>(Ahi + kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4))) = hi;
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
+            if (lane == 0) mbar_arrive(hi_full);
+            if (it >= 1) mbar_wait(lo_empty, (it - 1) & 1);
+#pragma unroll
+            for (int j = 0; j < kTcPoints / 16; j++) {
+                const int r = r0 + 16 * j;
+                uint4 lo;
+                lo.x = tf32_lo(v[j].x, tf32_hi(v[j].x)); lo.y = tf32_lo(v[j].y, tf32_hi(v[j].y));
+                lo.z = tf32_lo(v[j].z, tf32_hi(v[j].z)); lo.w = tf32_lo(v[j].w, tf32_hi(v[j].w));
+                *reinterpret_cast<uint4 *>(Alo + kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4))) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lo_full);
             if (pt == 0) TC_TRACE(4 + 4 * it);
         }
     } else {
@@ -667,7 +480,6 @@ conv5_finish_kernel(int b, int c, const float *__restrict__ vmax, const float *_
     }
 }
 
-constexpr size_t kLayerSmem = sizeof(float) * (2 * kTileP * kLdA + 2 * kKin * kLdW + 2 * kKin + 2 * kCols);
 
 }  // namespace
 
@@ -679,7 +491,7 @@ extern "C" int pnae_mlp_first(long long npts, const float *xyz, const float *w, 
     PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "mlp_first: unknown flag bits 0x%x", flags);
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * 64, st));
-    const int blocks = (int)min((npts + 15) / 16, (long long)pnae_sm_count() * 8);
+    const int blocks = (int)min((npts + 63) / 64, (long long)pnae_sm_count() * 8);
     PNAE_CUDA_OK(pnae_launch(mlp_first_kernel, dim3(blocks), dim3(256), 0, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0, npts, xyz, w, bias, out, stats));
     return PNAE_OK;
 }
@@ -701,32 +513,24 @@ extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in
     PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "mlp_layer: unknown flag bits 0x%x", flags);
     PNAE_REQUIRE(npts >= 1 && in && gamma_prev && beta_prev && moving_mean_prev && moving_var_prev && w && bias && out && stats && (!training || stats_prev),
                  "mlp_layer: invalid argument");
-    PNAE_REQUIRE(kin == kKin && kout >= kCols && kout % kCols == 0, "mlp_layer: needs 64 input channels and a multiple of 64 output channels (got %d -> %d)", kin, kout);
+    PNAE_REQUIRE(kin == kKin && (kout == 64 || kout == 128), "mlp_layer: needs 64 input channels and 64 or 128 output channels (got %d -> %d)", kin, kout);
     PNAE_REQUIRE(pnae_aligned(in, 16) && pnae_aligned(out, 8), "mlp_layer: in must be 16-byte and out 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     static bool configured[64] = {false};
     int dev = 0;
     PNAE_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
         PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         configured[dev] = true;
     }
-    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / kCols), st));     // statistics + tile counters
+    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / 64), st));
     const BnPrev bn = make_bn(stats_prev, (double)npts, gamma_prev, beta_prev, moving_mean_prev, moving_var_prev, eps, decay, training);
-    if ((kout == 64 || kout == 128) && getenv("PNAE_MLP_LEGACY") == nullptr) {
-        const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
-        const int gx = (int)min(ntiles, (long long)pnae_sm_count());
-        const bool pdl = (flags & PNAE_OVERLAP_PREVIOUS) != 0;
-        if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
-        else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
-        return PNAE_OK;
-    }
-    const long long ntiles = (npts + kTileP - 1) / kTileP;
-    const int gx = (int)min(ntiles, (long long)pnae_sm_count() * 3);
-    PNAE_CUDA_OK(pnae_launch(mlp_layer_kernel, dim3(gx, kout / kCols), dim3(kMlpThreads), kLayerSmem, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0,
-                             npts, kout, in, bn, w, bias, out, stats));
+    const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
+    const int gx = (int)min(ntiles, (long long)pnae_sm_count());            // persistent: one CTA per SM, tiles strided
+    const bool pdl = (flags & PNAE_OVERLAP_PREVIOUS) != 0;
+    if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
+    else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
     return PNAE_OK;
 }
 

@@ -249,6 +249,17 @@ PNAE_API int pnae_mlp_layer(long long npts, int kin /* 64 */, int kout /* 64 or 
                             const float *w, const float *bias, float *out, float *stats, int flags, void *stream);
 /* BatchNorm bookkeeping of one layer on its own (the layer kernels do this in their prologue; this entry exists for callers
  * that want the folded scale s = gamma/sqrt(var+eps) and shift t = beta - mean*s themselves). */
+/* Layer 1 folded into layer 2: y1 = xyz @ w1 + b1 is affine in xyz, so its BatchNorm statistics follow from the moments
+ * of xyz -- pnae_xyz_moments: moments (9 doubles, zero on entry unless the call zeroes them: flags) = the sums of x, y, z,
+ * xx, xy, xz, yy, yz, zz over all points -- and layer 2's kernel forms relu(BatchNorm1(y1)) on the fly from xyz.  Same
+ * results as pnae_mlp_first followed by pnae_mlp_layer up to the rounding of the statistics (double here), without the
+ * (npts, 64) tensor in between; moving_mean1 / moving_var1 are updated as pnae_mlp_layer would (training != 0). */
+PNAE_API int pnae_xyz_moments(long long npts, const float *xyz, double *moments /* (9) */, int flags, void *stream);
+PNAE_API int pnae_mlp_layer_xyz(long long npts, const float *xyz, const double *moments, const float *w1 /* (3,64) */,
+                                const float *b1, const float *gamma1, const float *beta1, float *moving_mean1,
+                                float *moving_var1, float eps, float decay, int training, int kout /* 64 or 128 */,
+                                const float *w /* (64,kout) */, const float *bias, float *out, float *stats, int flags,
+                                void *stream);
 PNAE_API int pnae_bn_fold(int k, const float *stats, double count, const float *gamma, const float *beta, float eps, float decay,
                           int training, float *moving_mean, float *moving_var, float *s_out, float *t_out, void *stream);
 /* relu(BatchNorm(y)) of the last of these layers (BatchNorm given like in pnae_mlp_layer) as the bf16 (npts, k) operand of

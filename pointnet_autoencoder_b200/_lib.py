@@ -52,6 +52,8 @@ SIGNATURES = {
     "pnae_match_cost_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pnae_match_cost_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnae_match_cost_factors": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnae_xyz_moments": (_i, [C.c_longlong, _vp, _vp, _i, _vp]),
+    "pnae_mlp_layer_xyz": (_i, [C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pnae_mlp_first": (_i, [C.c_longlong, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pnae_mlp_layer": (_i, [C.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pnae_conv5_finish": (_i, [_i, _i, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

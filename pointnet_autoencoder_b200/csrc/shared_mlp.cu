@@ -125,6 +125,35 @@ extern "C" __attribute__((visibility("default"))) int pnae_debug_mlp_trace(long 
 }
 #endif
 
+// Sums of x, y, z and of their six distinct products over all points, in double: what layer 1's BatchNorm statistics
+// follow from (mlp_layer_tc_kernel<.., true>).  One atomicAdd(double) per value and CTA; `moments` must be zero.
+__global__ void __launch_bounds__(256)
+xyz_moments_kernel(long long npts, const float *__restrict__ xyz, double *__restrict__ moments)
+{
+    __shared__ double s_part[8][9];
+    pnae_pdl_release();
+    pnae_pdl_wait();
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (long long)gridDim.x * blockDim.x) {
+        const double x = __ldg(xyz + p * 3), y = __ldg(xyz + p * 3 + 1), z = __ldg(xyz + p * 3 + 2);
+        a[0] += x; a[1] += y; a[2] += z;
+        a[3] += x * x; a[4] += x * y; a[5] += x * z; a[6] += y * y; a[7] += y * z; a[8] += z * z;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][i] = a[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double t = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < 8; wi++) t += s_part[wi][threadIdx.x];
+        atomicAdd(moments + threadIdx.x, t);
+    }
+}
+
 // Layers 2-4 on the fifth-generation tensor cores (tcgen05, kind::tf32, 3xTF32):
 //   D[channel, point] = W^T[channel, :] . a[point, :],   a = relu(s_prev * in + t_prev)
 // as  Whi.ahi + Wlo.ahi + Whi.alo  (hi = the value cut to TF32's 10 mantissa bits, lo = the remainder: fp32 accuracy,
@@ -144,7 +173,7 @@ constexpr int kTcProducerWarps = 8, kTcEpiWarps = 4;
 constexpr int kTcThreads = 32 * (1 + kTcProducerWarps + kTcEpiWarps);
 constexpr uint32_t kTcWBytes = 2 * kTcM * 128;         // one weight operand (two 32-element k boxes)
 constexpr uint32_t kTcABytes = 2 * kTcPoints * 128;    // one activation operand
-constexpr size_t kTcSmem = 1024 + 2 * kTcWBytes + 2 * kTcABytes + 256 + 2 * kKin * sizeof(float);
+constexpr size_t kTcSmem = 1024 + 2 * kTcWBytes + 2 * kTcABytes + 256 + 6 * kKin * sizeof(float);
 
 // byte offset of element (row, k) in a K-major SWIZZLE_128B operand of `rows` rows and 64 fp32 columns: two boxes of
 // 32 columns; inside a box a row is 128 bytes and its 16-byte chunks are XOR-ed with the row's position in its group of 8
@@ -153,9 +182,19 @@ __device__ __forceinline__ uint32_t tc_offset(int rows, int row, int k)
     return (uint32_t)((k >> 5) * rows * 128 + row * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4) + (k & 3) * 4);
 }
 
-template <int KOUT>
+// XYZ: the input rows are not read but computed -- layer 1 (3 -> 64) folded into this kernel's producers:
+//   y1 = xyz . W1 + b1  (three FMAs per channel, the arithmetic of mlp_first_kernel),  a = relu(s1 * y1 + t1),
+// with layer 1's BatchNorm statistics derived from the moments of xyz (xyz_moments_kernel): y1 is affine in xyz, so
+//   mean(y1_c) = w_c . mean(x) + b_c,   E[y1_c^2] = w_c^T E[x x^T] w_c + 2 b_c w_c . mean(x) + b_c^2.
+// The (B*N, 64) tensor of layer 1 is then neither written nor read.
+struct FirstLayer {
+    const float *xyz, *w1, *b1;          // (npts,3), (3,64), (64)
+    const double *moments;               // sum x, y, z, xx, xy, xz, yy, yz, zz over all points
+};
+
+template <int KOUT, bool XYZ>
 __global__ void __launch_bounds__(kTcThreads, 1)
-mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev bn, const float *__restrict__ w,
+mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const FirstLayer first, const BnPrev bn, const float *__restrict__ w,
                     const float *__restrict__ bias, float *__restrict__ out, float *__restrict__ stats)
 {
 #ifdef PNAE_MLP_TRACE
@@ -172,6 +211,7 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
     uint64_t *hi_full = bars, *lo_full = bars + 1, *hi_empty = bars + 2, *lo_empty = bars + 3, *t_full = bars + 4, *t_empty = bars + 6;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
     float *sp = reinterpret_cast<float *>(bars) + 64, *tp = sp + kKin;        // folded BatchNorm of the previous layer
+    float *w1s = tp + kKin;                                                   // (XYZ) layer 1's weights and bias: [4][64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
     constexpr int kout = KOUT;
@@ -205,8 +245,41 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
     if (threadIdx.x == 0) TC_TRACE(1);
     // everything above read only this layer's own parameters and may have run under the previous kernel's tail
     // (PNAE_OVERLAP_PREVIOUS); the input and its statistics belong to the time after it
+    if (XYZ && threadIdx.x < kKin) {
+        const int c = threadIdx.x;
+        w1s[c] = __ldg(first.w1 + c); w1s[64 + c] = __ldg(first.w1 + 64 + c); w1s[128 + c] = __ldg(first.w1 + 128 + c);
+        w1s[192 + c] = __ldg(first.b1 + c);
+    }
     pnae_pdl_wait();
-    if (threadIdx.x < kKin) bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0, sp[threadIdx.x], tp[threadIdx.x]);
+    if (threadIdx.x < kKin) {
+        if (XYZ) {
+            // layer 1's BatchNorm from the moments of xyz (double: the variance is a difference of second moments)
+            const int c = threadIdx.x;
+            float s, t;
+            if (bn.training) {
+                const double inv = 1.0 / (double)npts;
+                const double wx = w1s[c], wy = w1s[64 + c], wz = w1s[128 + c], b = w1s[192 + c];
+                const double *m = first.moments;
+                const double mx = m[0] * inv, my = m[1] * inv, mz = m[2] * inv;
+                const double lin = wx * mx + wy * my + wz * mz;
+                const double quad = wx * wx * m[3] + wy * wy * m[6] + wz * wz * m[8] + 2.0 * (wx * wy * m[4] + wx * wz * m[5] + wy * wz * m[7]);
+                const double mean = lin + b;
+                const double var = fmax(quad * inv + 2.0 * b * lin + b * b - mean * mean, 0.0);
+                if (blockIdx.x == 0) {
+                    bn.moving_mean[c] = fmaf(bn.decay, bn.moving_mean[c], (1.f - bn.decay) * (float)mean);
+                    bn.moving_var[c] = fmaf(bn.decay, bn.moving_var[c], (1.f - bn.decay) * (float)var);
+                }
+                s = bn.gamma[c] / sqrtf((float)var + bn.eps);
+                t = fmaf(-(float)mean, s, bn.beta[c]);
+            } else {
+                s = bn.gamma[c] / sqrtf(bn.moving_var[c] + bn.eps);
+                t = fmaf(-bn.moving_mean[c], s, bn.beta[c]);
+            }
+            sp[c] = s; tp[c] = t;
+        } else {
+            bn_fold_channel(bn, kKin, threadIdx.x, blockIdx.x == 0, sp[threadIdx.x], tp[threadIdx.x]);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -249,32 +322,54 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
         // ===== producers: a thread owns one 16-byte column chunk (4 input channels) of rows r0, r0 + 16, ... =====
         const int pt = threadIdx.x - 32;
         const int c4 = pt & 15, r0 = pt >> 4;
-        float s4[4], t4[4];
+        float s4[4], t4[4], wx1[4], wy1[4], wz1[4], bb1[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) { s4[e] = sp[4 * c4 + e]; t4[e] = tp[4 * c4 + e]; }
+        for (int e = 0; e < 4; e++) {
+            s4[e] = sp[4 * c4 + e]; t4[e] = tp[4 * c4 + e];
+            if (XYZ) { wx1[e] = w1s[4 * c4 + e]; wy1[e] = w1s[64 + 4 * c4 + e]; wz1[e] = w1s[128 + 4 * c4 + e]; bb1[e] = w1s[192 + 4 * c4 + e]; }
+            else { wx1[e] = wy1[e] = wz1[e] = bb1[e] = 0.f; }
+        }
         const uint32_t kbase = (uint32_t)((c4 >> 3) * kTcPoints * 128);
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const long long p0 = tile * kTcPoints;
-            float4 v[kTcPoints / 16];
+            // the activation of row j, chunk c4 from what was loaded: BatchNorm + ReLU of the raw input, or (XYZ) of layer 1
+            // computed on the spot
+            float4 v[XYZ ? 1 : kTcPoints / 16];
+            float px[XYZ ? kTcPoints / 16 : 1], py[XYZ ? kTcPoints / 16 : 1], pz[XYZ ? kTcPoints / 16 : 1];
 #pragma unroll
             for (int j = 0; j < kTcPoints / 16; j++) {
                 const long long row = min(p0 + r0 + 16 * j, npts - 1);         // rows past the end repeat the last row; the epilogue ignores them
-                v[j] = __ldg(reinterpret_cast<const float4 *>(in + row * kKin) + c4);
+                if (XYZ) {
+                    px[j] = __ldg(first.xyz + row * 3); py[j] = __ldg(first.xyz + row * 3 + 1); pz[j] = __ldg(first.xyz + row * 3 + 2);
+                } else {
+                    v[j] = __ldg(reinterpret_cast<const float4 *>(in + row * kKin) + c4);
+                }
             }
-            // BatchNorm + ReLU in place, then the two operand tiles one after the other, each behind its own barriers
-#pragma unroll
-            for (int j = 0; j < kTcPoints / 16; j++) {
-                v[j].x = fmaxf(fmaf(v[j].x, s4[0], t4[0]), 0.f); v[j].y = fmaxf(fmaf(v[j].y, s4[1], t4[1]), 0.f);
-                v[j].z = fmaxf(fmaf(v[j].z, s4[2], t4[2]), 0.f); v[j].w = fmaxf(fmaf(v[j].w, s4[3], t4[3]), 0.f);
-            }
+            auto act = [&](int j) -> float4 {
+                float4 a;
+                if (XYZ) {
+                    a.x = fmaf(pz[j], wz1[0], fmaf(py[j], wy1[0], fmaf(px[j], wx1[0], bb1[0])));
+                    a.y = fmaf(pz[j], wz1[1], fmaf(py[j], wy1[1], fmaf(px[j], wx1[1], bb1[1])));
+                    a.z = fmaf(pz[j], wz1[2], fmaf(py[j], wy1[2], fmaf(px[j], wx1[2], bb1[2])));
+                    a.w = fmaf(pz[j], wz1[3], fmaf(py[j], wy1[3], fmaf(px[j], wx1[3], bb1[3])));
+                } else {
+                    a = v[j];
+                }
+                a.x = fmaxf(fmaf(a.x, s4[0], t4[0]), 0.f); a.y = fmaxf(fmaf(a.y, s4[1], t4[1]), 0.f);
+                a.z = fmaxf(fmaf(a.z, s4[2], t4[2]), 0.f); a.w = fmaxf(fmaf(a.w, s4[3], t4[3]), 0.f);
+                return a;
+            };
+            // the two operand tiles one after the other, each behind its own barriers (the activation is cheap enough to
+            // form twice: keeping it would cost 64 registers)
             if (it >= 1) mbar_wait(hi_empty, (it - 1) & 1);
             if (pt == 0) TC_TRACE(3 + 4 * it);
 #pragma unroll
             for (int j = 0; j < kTcPoints / 16; j++) {
                 const int r = r0 + 16 * j;
+                const float4 a = act(j);
                 uint4 hi;
-                hi.x = tf32_hi(v[j].x); hi.y = tf32_hi(v[j].y); hi.z = tf32_hi(v[j].z); hi.w = tf32_hi(v[j].w);
+                hi.x = tf32_hi(a.x); hi.y = tf32_hi(a.y); hi.z = tf32_hi(a.z); hi.w = tf32_hi(a.w);
                 *reinterpret_cast<uint4 *>(Ahi + kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4))) = hi;
             }
             fence_proxy_async_smem();
@@ -284,9 +379,10 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const BnPrev b
 #pragma unroll
             for (int j = 0; j < kTcPoints / 16; j++) {
                 const int r = r0 + 16 * j;
+                const float4 a = act(j);
                 uint4 lo;
-                lo.x = tf32_lo(v[j].x, tf32_hi(v[j].x)); lo.y = tf32_lo(v[j].y, tf32_hi(v[j].y));
-                lo.z = tf32_lo(v[j].z, tf32_hi(v[j].z)); lo.w = tf32_lo(v[j].w, tf32_hi(v[j].w));
+                lo.x = tf32_lo(a.x, tf32_hi(a.x)); lo.y = tf32_lo(a.y, tf32_hi(a.y));
+                lo.z = tf32_lo(a.z, tf32_hi(a.z)); lo.w = tf32_lo(a.w, tf32_hi(a.w));
                 *reinterpret_cast<uint4 *>(Alo + kbase + (uint32_t)(r * 128 + (((c4 & 7) ^ (r & 7)) << 4))) = lo;
             }
             fence_proxy_async_smem();
@@ -496,6 +592,15 @@ extern "C" int pnae_mlp_first(long long npts, const float *xyz, const float *w, 
     return PNAE_OK;
 }
 
+static cudaError_t tc_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(mlp_layer_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_layer_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    return e;
+}
+
 static BnPrev make_bn(const float *stats, double count, const float *gamma, const float *beta, float *mm, float *mv, float eps,
                       float decay, int training)
 {
@@ -520,8 +625,7 @@ extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in
     int dev = 0;
     PNAE_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        PNAE_CUDA_OK(cudaFuncSetAttribute(mlp_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        PNAE_CUDA_OK(tc_configure());
         configured[dev] = true;
     }
     if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / 64), st));
@@ -529,8 +633,49 @@ extern "C" int pnae_mlp_layer(long long npts, int kin, int kout, const float *in
     const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
     const int gx = (int)min(ntiles, (long long)pnae_sm_count());            // persistent: one CTA per SM, tiles strided
     const bool pdl = (flags & PNAE_OVERLAP_PREVIOUS) != 0;
-    if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
-    else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, bn, w, bias, out, stats));
+    const FirstLayer none = {nullptr, nullptr, nullptr, nullptr};
+    if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64, false>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, none, bn, w, bias, out, stats));
+    else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128, false>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, in, none, bn, w, bias, out, stats));
+    return PNAE_OK;
+}
+
+extern "C" int pnae_xyz_moments(long long npts, const float *xyz, double *moments, int flags, void *stream)
+{
+    PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "xyz_moments: unknown flag bits 0x%x", flags);
+    PNAE_REQUIRE(npts >= 1 && xyz && moments && pnae_aligned(moments, 8), "xyz_moments: invalid argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(moments, 0, sizeof(double) * 9, st));
+    const int blocks = (int)min((npts + 255) / 256, (long long)pnae_sm_count());
+    PNAE_CUDA_OK(pnae_launch(xyz_moments_kernel, dim3(blocks), dim3(256), 0, st, (flags & PNAE_OVERLAP_PREVIOUS) != 0, npts, xyz, moments));
+    return PNAE_OK;
+}
+
+extern "C" int pnae_mlp_layer_xyz(long long npts, const float *xyz, const double *moments, const float *w1, const float *b1,
+                                  const float *gamma1, const float *beta1, float *moving_mean1, float *moving_var1,
+                                  float eps, float decay, int training, int kout, const float *w, const float *bias,
+                                  float *out, float *stats, int flags, void *stream)
+{
+    PNAE_REQUIRE((flags & ~(PNAE_STATS_ZEROED | PNAE_OVERLAP_PREVIOUS)) == 0, "mlp_layer_xyz: unknown flag bits 0x%x", flags);
+    PNAE_REQUIRE(npts >= 1 && xyz && w1 && b1 && gamma1 && beta1 && moving_mean1 && moving_var1 && w && bias && out && stats && (!training || moments),
+                 "mlp_layer_xyz: invalid argument");
+    PNAE_REQUIRE(kout == 64 || kout == 128, "mlp_layer_xyz: needs 64 or 128 output channels (got %d)", kout);
+    PNAE_REQUIRE(pnae_aligned(out, 8), "mlp_layer_xyz: out must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool configured[64] = {false};
+    int dev = 0;
+    PNAE_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        PNAE_CUDA_OK(tc_configure());
+        configured[dev] = true;
+    }
+    if (!(flags & PNAE_STATS_ZEROED)) PNAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (2 * kout + kout / 64), st));
+    const BnPrev bn = make_bn(nullptr, (double)npts, gamma1, beta1, moving_mean1, moving_var1, eps, decay, training);
+    const FirstLayer first = {xyz, w1, b1, moments};
+    const long long ntiles = (npts + kTcPoints - 1) / kTcPoints;
+    const int gx = (int)min(ntiles, (long long)pnae_sm_count());
+    const bool pdl = (flags & PNAE_OVERLAP_PREVIOUS) != 0;
+    if (kout == 64) PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<64, true>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, (const float *)nullptr, first, bn, w, bias, out, stats));
+    else PNAE_CUDA_OK(pnae_launch(mlp_layer_tc_kernel<128, true>, dim3(gx), dim3(kTcThreads), kTcSmem, st, pdl, npts, (const float *)nullptr, first, bn, w, bias, out, stats));
     return PNAE_OK;
 }
 

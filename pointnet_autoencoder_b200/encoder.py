@@ -175,21 +175,28 @@ class _EncoderChain(torch.autograd.Function):
         cnt = float(b * n)
 
         # Everything that is not one of the seven chain kernels first: conv5's bf16 weights and ONE zeroed arena for the
-        # four layers' statistics.  The seven then follow each other directly and each is enqueued as a programmatic
+        # layers' statistics.  The seven then follow each other directly and each is enqueued as a programmatic
         # dependent launch: its set-up (weights to shared memory, barriers, tensor memory) runs under its predecessor's tail.
         w5, b5, g5, be5, mm5, mv5 = layers[4]
         wtb = w5.detach().t().contiguous().to(torch.bfloat16)
-        words = [128] + [ops.mlp_stats_words(lay[0].shape[1]) for lay in layers[1:4]]
+        # arena: the 9 float64 moments of xyz first (18 words), then the statistics of layers 2-4
+        words = [18] + [ops.mlp_stats_words(lay[0].shape[1]) for lay in layers[1:4]]
         offs = [0]
         for wd in words:
             offs.append(offs[-1] + (wd + 3) // 4 * 4)
         arena = torch.zeros(offs[-1], dtype=torch.float32, device=x.device)
-        y, st = ops.mlp_first(x.detach(), layers[0][0].detach(), layers[0][1].detach(), stats_out=arena[offs[0]: offs[0] + words[0]], overlap=True)
-        prev = layers[0]
-        for i, lay in enumerate(layers[1:4], start=1):
+        view = lambda i: arena[offs[i]: offs[i] + words[i]]
+        # layer 1 is folded into layer 2's kernel: its BatchNorm statistics follow from the moments of xyz, and its
+        # (B*N,64) output is never written
+        l1, l2 = layers[0], layers[1]
+        mom = ops.xyz_moments(x.detach(), out=view(0).view(torch.float64), overlap=True) if training else None
+        y, st = ops.mlp_layer_xyz(x.detach(), mom, l1[0].detach(), l1[1].detach(), l1[2].detach(), l1[3].detach(), l1[4], l1[5],
+                                  training, decay, BN_EPS, l2[0].detach(), l2[1].detach(), stats_out=view(1), overlap=True)
+        prev = l2
+        for i, lay in enumerate(layers[2:4], start=2):
             # the previous layer's BatchNorm (+ moving-average update) and ReLU happen inside this layer's kernel
             y, st_next = ops.mlp_layer(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS,
-                                       lay[0].detach(), lay[1].detach(), stats_out=arena[offs[i]: offs[i] + words[i]], overlap=True)
+                                       lay[0].detach(), lay[1].detach(), stats_out=view(i), overlap=True)
             st, prev = st_next, lay
         xb = ops.mlp_apply_bf16(y, st, prev[2].detach(), prev[3].detach(), prev[4], prev[5], training, decay, BN_EPS, overlap=True).view(b, n, -1)
         need_arg = bool(grad_mode) and any(ctx.needs_input_grad)

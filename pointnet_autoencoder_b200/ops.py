@@ -297,6 +297,51 @@ def mlp_first(xyz, w, bias, stats_out=None, overlap=False):
     return out, stats.view(2, 64)
 
 
+def xyz_moments(xyz, out=None, overlap=False):
+    """xyz (B,N,3) fp32 -> (9,) float64: sums of x, y, z, xx, xy, xz, yy, yz, zz over all points (what layer 1's BatchNorm
+    statistics follow from, see mlp_layer_xyz).  out: a zeroed (9,) float64 view to accumulate into."""
+    _dev(xyz, "xyz")
+    _require(xyz.dim() == 3 and xyz.shape[2] == 3, "xyz_moments expects xyz (batch,#points,3)")
+    x = _f32c(xyz)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        if out is None:
+            mom, zf = torch.empty((9,), dtype=torch.float64, device=x.device), 0
+        else:
+            _require(out.dtype == torch.float64 and out.is_contiguous() and out.numel() == 9 and out.device == x.device,
+                     "out must be a contiguous zeroed float64 tensor of 9 elements on the input's device")
+            mom, zf = out, STATS_ZEROED
+        _lib.check(lib.pnae_xyz_moments(x.shape[0] * x.shape[1], _p(x), _p(mom), zf | (OVERLAP_PREVIOUS if overlap else 0), _stream(x)))
+    return mom
+
+
+def mlp_layer_xyz(xyz, moments, w1, b1, gamma1, beta1, moving_mean1, moving_var1, training, decay, eps, w, bias,
+                  stats_out=None, overlap=False):
+    """layers 1 and 2 in one kernel: relu(BatchNorm1(xyz @ w1 + b1)) @ w + bias -> raw output (B*N,kout) fp32, stats (2,kout),
+    with layer 1's batch statistics derived from `moments` (xyz_moments); the (B*N,64) tensor of layer 1 is never formed.
+    moving_mean1 / moving_var1 are updated in place when training."""
+    _dev(xyz, "xyz")
+    _require(xyz.dim() == 3 and xyz.shape[2] == 3 and tuple(w1.shape) == (3, 64) and tuple(b1.shape) == (64,) and w.shape[0] == 64
+             and tuple(bias.shape) == (w.shape[1],), "mlp_layer_xyz expects xyz (batch,#points,3), w1 (3,64), b1 (64,), w (64,kout), bias (kout,)")
+    kout = w.shape[1]
+    g, b = _bn_args(64, None, gamma1, beta1, moving_mean1, moving_var1, False)
+    if training:
+        _require(moments is not None and moments.dtype == torch.float64 and moments.numel() == 9 and moments.is_contiguous(),
+                 "mlp_layer_xyz needs the (9,) float64 moments of xyz in training mode")
+    ws = (w1, b1, w, bias)
+    x = _f32c(xyz); w1c = _f32c(_dev(w1, "w1")); b1c = _f32c(_dev(b1, "b1")); wc = _f32c(_dev(w, "w")); bc = _f32c(_dev(bias, "bias"))
+    npts = x.shape[0] * x.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        out = torch.empty((npts, kout), dtype=torch.float32, device=x.device)
+        buf, zf = _stats_arg(stats_out, 2 * kout + kout // 64, x.device)
+        _lib.check(lib.pnae_mlp_layer_xyz(npts, _p(x), _p(moments) if moments is not None else None, _p(w1c), _p(b1c), _p(g), _p(b),
+                                          _p(moving_mean1), _p(moving_var1), float(eps), float(decay), int(bool(training)), kout,
+                                          _p(wc), _p(bc), _p(out), _p(buf),
+                                          zf | _overlap_flag(overlap, *zip(ws, (w1c, b1c, wc, bc))), _stream(x)))
+    return out, buf[: 2 * kout].view(2, kout)
+
+
 def _bn_args(k, stats, gamma, beta, moving_mean, moving_var, training):
     _require(tuple(gamma.shape) == (k,) and tuple(beta.shape) == (k,) and tuple(moving_mean.shape) == (k,) and tuple(moving_var.shape) == (k,),
              "BatchNorm parameters must have one entry per input channel")

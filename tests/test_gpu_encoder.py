@@ -223,3 +223,28 @@ def test_encoder_chain_layers_1_to_4_match_the_library_path(training):
         if p_r.grad is None or float(p_r.grad.abs().max()) == 0.0 or (training and na.endswith(".bias")):
             continue          # (training-mode BN removes the mean: bias gradients are rounding noise around zero)
         assert scaled_err(p_a.grad, p_r.grad) < 5e-2, na
+
+
+@pytest.mark.parametrize("b,n,kout,training", [(32, 2048, 64, True), (3, 1000, 64, True), (2, 300, 128, True), (4, 512, 64, False)])
+def test_layer1_folded_into_layer2_matches_the_two_kernel_path(b, n, kout, training):
+    """pnae_xyz_moments + pnae_mlp_layer_xyz (layer 1 computed inside layer 2's producers, its BatchNorm statistics from
+    the moments of xyz) against pnae_mlp_first + pnae_mlp_layer: same output, same statistics, same moving averages."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    xyz = rnd(b, n, 3) * 0.6 + 0.3                      # off-centre: the variance is a difference of second moments
+    w1, b1 = rnd(3, 64), 0.5 * rnd(64)
+    gamma1, beta1 = 1.0 + 0.2 * rnd(64), 0.1 * rnd(64)
+    w2, b2 = rnd(64, kout) / 8, 0.1 * rnd(kout)
+    mm = [0.1 * rnd(64), None]; mv = [0.5 + torch.rand(64, device="cuda", generator=g), None]
+    mm[1], mv[1] = mm[0].clone(), mv[0].clone()
+    y1, st1 = ops.mlp_first(xyz, w1, b1)
+    ref, ref_st = ops.mlp_layer(y1, st1, gamma1, beta1, mm[0], mv[0], training, 0.9, 1e-3, w2, b2)
+    mom = ops.xyz_moments(xyz) if training else None
+    if training:                                        # the moments themselves, against float64 sums
+        x64 = xyz.double().reshape(-1, 3)
+        want = torch.cat([x64.sum(0), (x64[:, 0:1] * x64).sum(0), (x64[:, 1:2] * x64[:, 1:]).sum(0), (x64[:, 2] ** 2).sum().view(1)])
+        assert float((mom - want).abs().max() / want.abs().max()) < 1e-12
+    out, st = ops.mlp_layer_xyz(xyz, mom, w1, b1, gamma1, beta1, mm[1], mv[1], training, 0.9, 1e-3, w2, b2)
+    assert scaled_err(out, ref) < 2e-5
+    assert scaled_err(st, ref_st) < 2e-5
+    assert scaled_err(mm[1], mm[0]) < 1e-5 and scaled_err(mv[1], mv[0]) < 1e-5

@@ -307,10 +307,14 @@ def run_product(args):
                     self.rem[r] = ChamferStep([x1[RING - 1 - j] for j in range(r)], [x2[RING - 1 - j] for j in range(r)], g1, g2, **self.kw)
                 self.rem[r].run()
 
-    ring = Ring(fused=True)                                        # the benchmarked two-kernel step
-    ring3 = Ring(share_buffers_with=ring.share)                    # the three-kernel form
-    ring_fwd = Ring(forward_only=True, share_buffers_with=ring.share)   # the dominant kernel pair alone (sweep + finalize), for the roofline figure
-    for r_ in (ring, ring3, ring_fwd):                             # build the remainder graphs outside the timed region
+    # the benchmarked step: two kernels per step, software-pipelined inside each graph (step s+1's sweep runs while step
+    # s's finalize + gradient resolve; alternating output sets and workspaces, pnae_chamfer_graph_create_pipelined)
+    ring = Ring(fused=True, pipelined=True)
+    ring_seq = Ring(fused=True, share_buffers_with=ring.share)     # the same steps strictly one after the other
+    ring3 = Ring(share_buffers_with=ring.share)                    # the three-kernel form, sequential
+    ring_fwd = Ring(forward_only=True, pipelined=True, share_buffers_with=ring.share)   # the dominant kernel pair alone (sweep + finalize), for the roofline figure
+    ring_fwd_seq = Ring(forward_only=True, share_buffers_with=ring.share)
+    for r_ in (ring, ring_seq, ring3, ring_fwd, ring_fwd_seq):     # build the remainder graphs outside the timed region
         r_.run(args.steps % SPG); r_.run(args.warmup % SPG)
     slots = ring.full
 
@@ -343,6 +347,10 @@ def run_product(args):
     barrier()
     ev_fwd = timed_windows(ring_fwd, WINDOWS)        # forward alone, same ring, same clocks
     barrier()
+    ev_seq = timed_windows(ring_seq, WINDOWS)
+    barrier()
+    ev_fwd_seq = timed_windows(ring_fwd_seq, WINDOWS)
+    barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
     med = lambda evs: float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]))
@@ -350,6 +358,8 @@ def run_product(args):
     ms = float(np.median(win_ms))
     three_ms = med(ev_three) / args.steps
     fwd_ms = med(ev_fwd) / args.steps
+    seq_ms = med(ev_seq) / args.steps
+    fwd_seq_ms = med(ev_fwd_seq) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -471,7 +481,7 @@ def run_product(args):
         "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
                    "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                    "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB) > 126 MB L2; outputs and workspace are reused" % (RING, RING * 12 * B * (N + M) / 1e6),
-                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps, plus one shorter graph when K is not a multiple of %d" % (SPG, SPG, SPG),
+                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps, plus one shorter graph when K is not a multiple of %d; inside a graph the steps are software-pipelined: step s+1's sweep runs while step s's finalize resolves, on alternating output sets and workspaces (every step's results are complete; extra.sequential_step_ms is the same work strictly in order)" % (SPG, SPG, SPG),
                    "timing": "%d back-to-back windows of %d steps, CUDA events on the launching stream; value = median window, max over ranks" % (WINDOWS, args.steps),
                    "upstream_grad": "100/(B*N) (models/model.py:81-83), passed as grad_dist arrays",
                    "host_cores_of_rank0": len(cores) if cores else None},
@@ -483,8 +493,11 @@ def run_product(args):
                      # the same launch against the FFMA rate measured in this run (pnae_fp32_probe), None if the probe failed
                      "peak_ffma_measured": ffma_tflops, "frac_of_ffma_measured": (achieved / ffma_tflops) if ffma_tflops else None,
                      "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs, "kernel_ms": fwd_ms,
+                     # the same two kernels with every step's finalize finished before the next sweep starts
+                     "kernel_ms_sequential": fwd_seq_ms, "frac_sequential": FLOP_PER_PAIR * pairs / (fwd_seq_ms * 1e-3) / 1e12 / fp32_peak,
                      # the same FLOPs over the whole fwd+grad step (gradient FLOPs counted as 0)
                      "fwd_grad_step_frac": FLOP_PER_PAIR * pairs / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                     "fwd_grad_step_frac_sequential": FLOP_PER_PAIR * pairs / (seq_ms * 1e-3) / 1e12 / fp32_peak,
                      "fwd_grad_step_frac_three_kernel_form": FLOP_PER_PAIR * pairs / (three_ms * 1e-3) / 1e12 / fp32_peak,
                      "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
@@ -504,6 +517,8 @@ def run_product(args):
         "clocks": clocks,
         "check": check,
     }
+    extra["sequential_step_ms"] = seq_ms
+    extra["sequential_step_gpairs"] = pairs * world / (seq_ms * 1e-3) / 1e9
     extra["three_kernel_step_ms"] = three_ms
     extra["three_kernel_step_gpairs"] = pairs * world / (three_ms * 1e-3) / 1e9
     if world == 1 and not args.no_cpu_baseline:
@@ -733,7 +748,7 @@ def main():
     ap.add_argument("--no-emd", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the autoencoder training-step figure (BASELINE configs[3])")
     ap.add_argument("--no-refgpu", action="store_true", help="skip timing the reference's own CUDA kernels")
-    ap.add_argument("--steps-per-graph", type=int, default=8, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches); a shorter graph covers the remainder, so exactly --steps steps are timed per window")
+    ap.add_argument("--steps-per-graph", type=int, default=32, help="consecutive steps captured in one CUDA graph (must divide the ring of 128 batches); a shorter graph covers the remainder, so exactly --steps steps are timed per window")
     ap.add_argument("--max-seconds", type=float, default=1200.0, help="hard wall-clock limit: exit with status 3 instead of hanging a GPU box (0 = none)")
     args = ap.parse_args()
     if args.max_seconds > 0:

@@ -23,7 +23,10 @@ class ChamferStep:
     tensors, overwritten by every run).  To feed new data, copy into `.xyz1` / `.xyz2`."""
 
     def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None, outputs=None,
-                 fused=False):
+                 fused=False, pipelined=False):
+        # pipelined (multi-step graphs): step s+1's sweep runs while step s's finalize / gradient resolve
+        # (pnae_chamfer_graph_create_pipelined).  Steps alternate between two output sets and two workspaces; the public
+        # attributes (.dist1 ...) are the set the LAST step wrote, `.other` holds the set of the step before it.
         # fused: NnDistance + NnDistanceGrad through pnae_nn_distance_fwd_grad (sweep + finalize, the finalize also
         # forms the gradients) instead of the three-kernel pnae_nn_distance_fwd -> pnae_nn_distance_bwd sequence
         self.fused = bool(fused) and not forward_only
@@ -59,15 +62,40 @@ class ChamferStep:
             self.dist1 = torch.empty((b, n), **f32); self.idx1 = torch.empty((b, n), **i32)
             self.dist2 = torch.empty((b, m), **f32); self.idx2 = torch.empty((b, m), **i32)
             self.grad_xyz1 = torch.empty((b, n, 3), **f32); self.grad_xyz2 = torch.empty((b, m, 3), **f32)
+        self.pipelined = bool(pipelined) and self.steps >= 2
+        names = ("dist1", "idx1", "dist2", "idx2", "grad_xyz1", "grad_xyz2")
         with torch.cuda.device(dev):
             wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
             if o is None:
                 self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+            if self.pipelined:
+                if o is not None and getattr(o, "other", None) is not None:
+                    self.other = o.other
+                else:
+                    self.other = {k: torch.empty_like(getattr(self, k)) for k in names}
+                    self.other["ws"] = torch.empty_like(self.ws)
+            else:
+                self.other = None
             torch.cuda.synchronize(dev)
             h = C.c_void_p()
             p = lambda t: C.c_void_p(t.data_ptr())
             arr1 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi1])
             arr2 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi2])
+            if self.pipelined:
+                last = (self.steps - 1) & 1          # the set the last step writes = the public attributes
+                def pair(k):
+                    mine, oth = (getattr(self, k) if k != "ws" else self.ws), self.other[k]
+                    sets = [oth, oth]
+                    sets[last] = mine
+                    return (C.c_void_p * 2)(sets[0].data_ptr(), sets[1].data_ptr())
+                none2 = None
+                _lib.check(lib.pnae_chamfer_graph_create_pipelined(
+                    int(self.fused), self.steps, b, n, arr1, m, arr2, pair("dist1"), pair("idx1"), pair("dist2"), pair("idx2"),
+                    p(self.g1), p(self.g2), none2 if forward_only else pair("grad_xyz1"), none2 if forward_only else pair("grad_xyz2"),
+                    pair("ws"), wsb, C.byref(h)))
+                self._h = h
+                self._lib = lib
+                return
             create = lib.pnae_chamfer_graph_create_fused_multi if self.fused else lib.pnae_chamfer_graph_create_multi
             _lib.check(create(self.steps, b, n, arr1, m, arr2, p(self.dist1), p(self.idx1),
                               p(self.dist2), p(self.idx2), p(self.g1), p(self.g2),

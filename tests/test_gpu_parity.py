@@ -165,6 +165,31 @@ def test_chamfer_graph_step_equals_eager_calls():
     assert torch.equal(step.dist1, ops.nn_distance_fwd(other, x2)[0])
 
 
+@pytest.mark.parametrize("mode", ["fused", "three_kernels", "forward_only"])
+@pytest.mark.parametrize("steps,b,n,m", [(5, 3, 700, 900), (2, 32, 2048, 2048), (6, 2, 300, 4100)])
+def test_pipelined_graph_gives_every_step_the_sequential_results(mode, steps, b, n, m):
+    """pnae_chamfer_graph_create_pipelined: step s+1's sweep runs while step s's finalize resolves, on alternating
+    output sets and workspaces.  The last two steps' results (the two sets) must be those of eager calls on their
+    inputs, after one replay and after three."""
+    from pointnet_autoencoder_b200.graphs import ChamferStep
+    ins = [clouds("randn", b, n, m, seed=40 + s) for s in range(steps)]
+    x1 = [cu(a) for a, _ in ins]; x2 = [cu(c) for _, c in ins]
+    step = ChamferStep(x1, x2, fused=(mode == "fused"), forward_only=(mode == "forward_only"), pipelined=True)
+    assert step.pipelined and step.other is not None
+    for runs in (1, 2):
+        for _ in range(runs):
+            step.run()
+        torch.cuda.synchronize()
+        for s, got in ((steps - 1, {k: getattr(step, k) for k in ("dist1", "idx1", "dist2", "idx2", "grad_xyz1", "grad_xyz2")}),
+                       (steps - 2, step.other)):
+            d1, i1, d2, i2 = ops.nn_distance_fwd(x1[s], x2[s])
+            assert torch.equal(got["dist1"], d1) and torch.equal(got["idx1"], i1)
+            assert torch.equal(got["dist2"], d2) and torch.equal(got["idx2"], i2)
+            if mode != "forward_only":
+                g1, g2 = ops.nn_distance_bwd(x1[s], x2[s], step.g1, i1, step.g2, i2)
+                assert torch.allclose(got["grad_xyz1"], g1, rtol=1e-4, atol=1e-8) and torch.allclose(got["grad_xyz2"], g2, rtol=1e-4, atol=1e-8)
+
+
 def test_wide_index_span_arithmetic_matches_oracle():
     """The sweep computes its spans and slot ranks in 32 bits when the launch fits and in 64 bits otherwise;
     PNAE_NN_INDEX64 forces the wide path at a size the oracle can check (separate process: the switch is read once)."""

@@ -24,6 +24,7 @@ struct Set {
     char *d_out, *h_out;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
+    void *pipelined;             // pnae_chamfer_graph_create_pipelined handle (fused sets with room for two workspaces), else NULL
     cudaEvent_t ev_in, ev_run, ev_out;
     bool busy;
 };
@@ -39,6 +40,7 @@ struct HostPipeline {
 void destroy(HostPipeline *hp)
 {
     for (Set &s : hp->sets) {
+        if (s.pipelined) pnae_graph_destroy(s.pipelined);
         if (s.exec) cudaGraphExecDestroy(s.exec);
         if (s.graph) cudaGraphDestroy(s.graph);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
@@ -59,6 +61,25 @@ void destroy(HostPipeline *hp)
 static int capture_set(HostPipeline *hp, Set &s, int fused, const size_t *off, const float *gd1, const float *gd2,
                        void *workspace, size_t workspace_bytes)
 {
+    // Several fused steps and a workspace twice the size of one: the software-pipelined graph (step k+1's sweep runs while
+    // step k's finalize resolves; every step has its own result block, the two workspace halves alternate).
+    const size_t one = pnae_nn_distance_workspace_bytes(hp->b, hp->n, hp->m);
+    const size_t half = (one + 255) & ~(size_t)255;
+    if (fused && hp->steps >= 2 && workspace_bytes >= half + one) {
+        std::vector<const float *> x1(hp->steps), x2(hp->steps);
+        std::vector<float *> g1(hp->steps), g2(hp->steps), d1(hp->steps), d2(hp->steps);
+        std::vector<int *> i1(hp->steps), i2(hp->steps);
+        for (int k = 0; k < hp->steps; k++) {
+            char *o = s.d_out + (size_t)k * hp->out_stride;
+            x1[k] = s.d_xyz1 + (size_t)k * hp->b * hp->n * 3; x2[k] = s.d_xyz2 + (size_t)k * hp->b * hp->m * 3;
+            g1[k] = (float *)(o + off[0]); g2[k] = (float *)(o + off[1]);
+            d1[k] = (float *)(o + off[2]); i1[k] = (int *)(o + off[3]);
+            d2[k] = (float *)(o + off[4]); i2[k] = (int *)(o + off[5]);
+        }
+        void *ws2[2] = {workspace, (char *)workspace + half};
+        return pnae_chamfer_graph_create_pipelined(1, hp->steps, hp->steps, hp->b, hp->n, x1.data(), hp->m, x2.data(), d1.data(), i1.data(),
+                                                   d2.data(), i2.data(), gd1, gd2, g1.data(), g2.data(), ws2, one, &s.pipelined);
+    }
     cudaStream_t st;
     PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
@@ -161,7 +182,8 @@ extern "C" int pnae_chamfer_host_pipeline_submit(void *handle, const float *h_xy
     PNAE_CUDA_OK(cudaMemcpyAsync(s.d_xyz2, h_xyz2, hp->in2_bytes, cudaMemcpyHostToDevice, hp->s_in));
     PNAE_CUDA_OK(cudaEventRecord(s.ev_in, hp->s_in));
     PNAE_CUDA_OK(cudaStreamWaitEvent(hp->s_run, s.ev_in, 0));
-    PNAE_CUDA_OK(cudaGraphLaunch(s.exec, hp->s_run));
+    if (s.pipelined) { const int rc = pnae_graph_launch(s.pipelined, hp->s_run); if (rc) return rc; }
+    else PNAE_CUDA_OK(cudaGraphLaunch(s.exec, hp->s_run));
     PNAE_CUDA_OK(cudaEventRecord(s.ev_run, hp->s_run));
     PNAE_CUDA_OK(cudaStreamWaitEvent(hp->s_out, s.ev_run, 0));
     if (hp->d2h_bytes == hp->out_stride || hp->steps == 1)

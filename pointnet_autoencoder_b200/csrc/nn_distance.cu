@@ -978,9 +978,9 @@ extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m,
 // Software-pipelined form of the multi-step graph: step s+1's sweep follows step s's sweep directly and runs WHILE step
 // s's finalize (and gradient) resolve on a second captured stream.  The sweep is compute-bound and the finalize
 // latency-bound (two dependent L2 round trips per point), so together they cost little more than the sweep alone.  Steps
-// alternate between two output sets and two workspaces; step s+2's sweep waits for step s's finalize (it reuses that
-// workspace and zeroes those gradients).
-extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int b, int n, const float *const *xyz1, int m,
+// cycle through `nsets` >= 2 output sets and alternate between two workspaces; step s+2's sweep waits for step s's finalize
+// (it reuses that workspace and, with two sets, zeroes those gradients).
+extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nsets, int b, int n, const float *const *xyz1, int m,
                                                    const float *const *xyz2, float *const *dist1, int *const *idx1,
                                                    float *const *dist2, int *const *idx2,
                                                    const float *grad_dist1, const float *grad_dist2,
@@ -989,14 +989,15 @@ extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int b, 
 {
     PNAE_REQUIRE(handle != nullptr, "chamfer_graph_create_pipelined: NULL handle");
     *handle = nullptr;
-    PNAE_REQUIRE(steps >= 1 && b >= 1 && n >= 1 && m >= 1 && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && workspace,
-                 "chamfer_graph_create_pipelined: invalid argument");
+    PNAE_REQUIRE(steps >= 1 && nsets >= 2 && b >= 1 && n >= 1 && m >= 1 && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && workspace,
+                 "chamfer_graph_create_pipelined: invalid argument (at least two output sets)");
     const bool grads = grad_xyz1 != nullptr && grad_xyz2 != nullptr;
     PNAE_REQUIRE(!fused || grads, "chamfer_graph_create_pipelined: the fused form needs gradient outputs");
     PNAE_REQUIRE(!grads || (grad_dist1 && grad_dist2), "chamfer_graph_create_pipelined: upstream gradients are required with gradient outputs");
-    for (int k = 0; k < 2; k++)
-        PNAE_REQUIRE(dist1[k] && idx1[k] && dist2[k] && idx2[k] && workspace[k] && (!grads || (grad_xyz1[k] && grad_xyz2[k])),
-                     "chamfer_graph_create_pipelined: two complete output sets and two workspaces are required");
+    for (int k = 0; k < nsets; k++)
+        PNAE_REQUIRE(dist1[k] && idx1[k] && dist2[k] && idx2[k] && (!grads || (grad_xyz1[k] && grad_xyz2[k])),
+                     "chamfer_graph_create_pipelined: every output set must be complete");
+    PNAE_REQUIRE(workspace[0] && workspace[1] && workspace[0] != workspace[1], "chamfer_graph_create_pipelined: two workspaces are required");
     cudaStream_t st, fin;
     PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (cudaStreamCreateWithFlags(&fin, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(st); pnae_set_error("cudaStreamCreate failed"); return PNAE_ERR_CUDA; }
@@ -1020,15 +1021,15 @@ extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int b, 
 #endif
         const int ctas = PNAE_NN_PIPE_CTAS;
         for (int s = 0; s < steps && rc == PNAE_OK; s++) {
-            const int k = s & 1;
+            const int k = s % nsets, wk = s & 1;      // output set, workspace
             cudaEvent_t swept = ev[2 * s], done = ev[2 * s + 1];
             if (s >= 2 && cudaStreamWaitEvent(st, ev[2 * (s - 2) + 1], 0) != cudaSuccess) { pnae_set_error("cudaStreamWaitEvent failed"); rc = PNAE_ERR_CUDA; break; }
             if (fused) {
                 rc = launch_fwd("chamfer_graph_create_pipelined", b, n, xyz1[s], m, xyz2[s], dist1[k], idx1[k], dist2[k], idx2[k], nullptr,
-                                grad_xyz1[k], grad_xyz2[k], 0.f, 0.f, grad_dist1, grad_dist2, workspace[k], workspace_bytes, st, ctas, fin, swept);
+                                grad_xyz1[k], grad_xyz2[k], 0.f, 0.f, grad_dist1, grad_dist2, workspace[wk], workspace_bytes, st, ctas, fin, swept);
             } else {
                 rc = launch_fwd("chamfer_graph_create_pipelined", b, n, xyz1[s], m, xyz2[s], dist1[k], idx1[k], dist2[k], idx2[k], nullptr,
-                                nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, workspace[k], workspace_bytes, st, ctas, fin, swept);
+                                nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, workspace[wk], workspace_bytes, st, ctas, fin, swept);
                 if (rc == PNAE_OK && grads)
                     rc = pnae_nn_distance_bwd(b, n, xyz1[s], m, xyz2[s], grad_dist1, idx1[k], grad_dist2, idx2[k], grad_xyz1[k], grad_xyz2[k], fin);
             }

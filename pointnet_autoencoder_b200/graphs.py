@@ -90,7 +90,7 @@ class ChamferStep:
                     return (C.c_void_p * 2)(sets[0].data_ptr(), sets[1].data_ptr())
                 none2 = None
                 _lib.check(lib.pnae_chamfer_graph_create_pipelined(
-                    int(self.fused), self.steps, b, n, arr1, m, arr2, pair("dist1"), pair("idx1"), pair("dist2"), pair("idx2"),
+                    int(self.fused), self.steps, 2, b, n, arr1, m, arr2, pair("dist1"), pair("idx1"), pair("dist2"), pair("idx2"),
                     p(self.g1), p(self.g2), none2 if forward_only else pair("grad_xyz1"), none2 if forward_only else pair("grad_xyz2"),
                     pair("ws"), wsb, C.byref(h)))
                 self._h = h

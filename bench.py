@@ -481,7 +481,7 @@ def run_product(args):
         "config": {"workload": "nn_distance fwd+grad B=%d N=M=%d per GPU (BASELINE.json configs[1])" % (B, N),
                    "pairs_per_step_per_gpu": pairs, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                    "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB) > 126 MB L2; outputs and workspace are reused" % (RING, RING * 12 * B * (N + M) / 1e6),
-                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps, plus one shorter graph when K is not a multiple of %d; inside a graph the steps are software-pipelined: step s+1's sweep runs while step s's finalize resolves, on alternating output sets and workspaces (every step's results are complete; extra.sequential_step_ms is the same work strictly in order)" % (SPG, SPG, SPG),
+                   "launch": "CUDA graphs of %d consecutive steps (2 kernels per step: sweep, finalize+gradient; pnae_nn_distance_fwd_grad), one replay per %d steps, plus one shorter graph when K is not a multiple of %d; inside a graph the steps are software-pipelined: step s+1's sweep runs while step s's finalize resolves, on three rotating output sets and workspaces (every step's results are complete; extra.sequential_step_ms is the same work strictly in order)" % (SPG, SPG, SPG),
                    "timing": "%d back-to-back windows of %d steps, CUDA events on the launching stream; value = median window, max over ranks" % (WINDOWS, args.steps),
                    "upstream_grad": "100/(B*N) (models/model.py:81-83), passed as grad_dist arrays",
                    "host_cores_of_rank0": len(cores) if cores else None},

@@ -127,14 +127,14 @@ PNAE_API int pnae_chamfer_graph_create_fused_multi(int steps, int b, int n, cons
                                                    float *grad_xyz1, float *grad_xyz2,
                                                    void *workspace, size_t workspace_bytes, void **handle);
 /* The multi-step graph, software-pipelined: step s+1's sweep runs while step s's finalize (and gradient) resolve.  Steps
- * cycle through `nsets` >= 2 output sets and alternate between TWO workspaces (each of pnae_nn_distance_workspace_bytes):
- * the output pointer lists have `nsets` entries, `workspace` two, xyz1 / xyz2 `steps`; step s writes set s % nsets -- with
- * two sets the last step's results are in set (steps - 1) % 2 after a launch and the one before it in the other; with
- * nsets == steps every step keeps its own results.  fused != 0: sweep + finalize-with-gradients
+ * cycle through `nsets` >= 2 output sets and `nws` workspaces, 2 <= nws <= nsets (each of pnae_nn_distance_workspace_bytes):
+ * the output pointer lists have `nsets` entries, `workspace` has `nws`, xyz1 / xyz2 `steps`; step s writes set s % nsets
+ * -- after a launch the last step's results are in set (steps - 1) % nsets, the one before it in the set before that;
+ * with nsets == steps every step keeps its own results.  Three workspaces let the sweeps follow each other without a gap.  fused != 0: sweep + finalize-with-gradients
  * (pnae_nn_distance_fwd_grad); fused == 0: pnae_nn_distance_fwd, plus pnae_nn_distance_bwd when gradient outputs are
  * given.  Results are those of the sequential graph, step for step.  The whole batch must fit one launch
  * (pnae_nn_distance_plan: be == b). */
-PNAE_API int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nsets, int b, int n, const float *const *xyz1, int m,
+PNAE_API int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nsets, int nws, int b, int n, const float *const *xyz1, int m,
                                                  const float *const *xyz2, float *const *dist1, int *const *idx1,
                                                  float *const *dist2, int *const *idx2,
                                                  const float *grad_dist1, const float *grad_dist2,

@@ -76,8 +76,10 @@ static int capture_set(HostPipeline *hp, Set &s, int fused, const size_t *off, c
             d1[k] = (float *)(o + off[2]); i1[k] = (int *)(o + off[3]);
             d2[k] = (float *)(o + off[4]); i2[k] = (int *)(o + off[5]);
         }
-        void *ws2[2] = {workspace, (char *)workspace + half};
-        return pnae_chamfer_graph_create_pipelined(1, hp->steps, hp->steps, hp->b, hp->n, x1.data(), hp->m, x2.data(), d1.data(), i1.data(),
+        // three workspaces when there is room (and at least three steps): the sweeps then follow each other without a gap
+        const int nws = (hp->steps >= 3 && workspace_bytes >= 2 * half + one) ? 3 : 2;
+        void *ws2[3] = {workspace, (char *)workspace + half, (char *)workspace + 2 * half};
+        return pnae_chamfer_graph_create_pipelined(1, hp->steps, hp->steps, nws, hp->b, hp->n, x1.data(), hp->m, x2.data(), d1.data(), i1.data(),
                                                    d2.data(), i2.data(), gd1, gd2, g1.data(), g2.data(), ws2, one, &s.pipelined);
     }
     cudaStream_t st;

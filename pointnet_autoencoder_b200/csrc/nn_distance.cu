@@ -978,9 +978,11 @@ extern "C" int pnae_chamfer_graph_create(int b, int n, const float *xyz1, int m,
 // Software-pipelined form of the multi-step graph: step s+1's sweep follows step s's sweep directly and runs WHILE step
 // s's finalize (and gradient) resolve on a second captured stream.  The sweep is compute-bound and the finalize
 // latency-bound (two dependent L2 round trips per point), so together they cost little more than the sweep alone.  Steps
-// cycle through `nsets` >= 2 output sets and alternate between two workspaces; step s+2's sweep waits for step s's finalize
-// (it reuses that workspace and, with two sets, zeroes those gradients).
-extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nsets, int b, int n, const float *const *xyz1, int m,
+// cycle through `nsets` >= 2 output sets and `nws` >= 2 workspaces (nws <= nsets); step s+nws's sweep waits for step s's
+// finalize (it reuses that workspace and, with nsets == nws, zeroes those gradients).  With two workspaces a sweep still
+// waits for the finalize of the step before the previous one, which cannot get SM slots before the previous sweep retires:
+// 48.2 us per fused step at B=32, N=M=2048; with three the sweeps follow each other without a gap.
+extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nsets, int nws, int b, int n, const float *const *xyz1, int m,
                                                    const float *const *xyz2, float *const *dist1, int *const *idx1,
                                                    float *const *dist2, int *const *idx2,
                                                    const float *grad_dist1, const float *grad_dist2,
@@ -989,15 +991,16 @@ extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nse
 {
     PNAE_REQUIRE(handle != nullptr, "chamfer_graph_create_pipelined: NULL handle");
     *handle = nullptr;
-    PNAE_REQUIRE(steps >= 1 && nsets >= 2 && b >= 1 && n >= 1 && m >= 1 && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && workspace,
-                 "chamfer_graph_create_pipelined: invalid argument (at least two output sets)");
+    PNAE_REQUIRE(steps >= 1 && nsets >= 2 && nws >= 2 && nws <= nsets && b >= 1 && n >= 1 && m >= 1 && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2 && workspace,
+                 "chamfer_graph_create_pipelined: invalid argument (at least two output sets and two workspaces, no more workspaces than sets)");
     const bool grads = grad_xyz1 != nullptr && grad_xyz2 != nullptr;
     PNAE_REQUIRE(!fused || grads, "chamfer_graph_create_pipelined: the fused form needs gradient outputs");
     PNAE_REQUIRE(!grads || (grad_dist1 && grad_dist2), "chamfer_graph_create_pipelined: upstream gradients are required with gradient outputs");
     for (int k = 0; k < nsets; k++)
         PNAE_REQUIRE(dist1[k] && idx1[k] && dist2[k] && idx2[k] && (!grads || (grad_xyz1[k] && grad_xyz2[k])),
                      "chamfer_graph_create_pipelined: every output set must be complete");
-    PNAE_REQUIRE(workspace[0] && workspace[1] && workspace[0] != workspace[1], "chamfer_graph_create_pipelined: two workspaces are required");
+    for (int k = 0; k < nws; k++)
+        PNAE_REQUIRE(workspace[k] != nullptr && (k == 0 || workspace[k] != workspace[0]), "chamfer_graph_create_pipelined: %d distinct workspaces are required", nws);
     cudaStream_t st, fin;
     PNAE_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (cudaStreamCreateWithFlags(&fin, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(st); pnae_set_error("cudaStreamCreate failed"); return PNAE_ERR_CUDA; }
@@ -1013,17 +1016,19 @@ extern "C" int pnae_chamfer_graph_create_pipelined(int fused, int steps, int nse
     }
     if (rc == PNAE_OK) {
         // Sweep CTAs per SM in this form: two.  The sweep's inner loop is bound by the FP32 pipe, which eight warps per SM
-        // already fill, and half the register file stays free for the previous step's finalize CTAs to be resident
-        // beside it.  Measured per fused step (B=32, N=M=2048; 52.8 us sequential): four CTAs 48.2 us (the finalize only
-        // finds slots as sweep CTAs retire), three 56.3 us, two 46.7 us, one 140 us.
+        // already fill, and half the register file stays free for the previous steps' finalize CTAs to be resident
+        // beside it.  Measured per fused step (B=32, N=M=2048; 52.8 us sequential) with three workspaces: two CTAs 46.4 us
+        // in every window of every run length; four 48.4 us (the finalize only finds slots as sweep CTAs retire).  With
+        // two workspaces two CTAs measured anything from 46.6 to 62 us from window to window, four a steady 48.2 us.
 #ifndef PNAE_NN_PIPE_CTAS
 #define PNAE_NN_PIPE_CTAS 2
 #endif
         const int ctas = PNAE_NN_PIPE_CTAS;
         for (int s = 0; s < steps && rc == PNAE_OK; s++) {
-            const int k = s % nsets, wk = s & 1;      // output set, workspace
+            const int k = s % nsets, wk = s % nws;    // output set, workspace
             cudaEvent_t swept = ev[2 * s], done = ev[2 * s + 1];
-            if (s >= 2 && cudaStreamWaitEvent(st, ev[2 * (s - 2) + 1], 0) != cudaSuccess) { pnae_set_error("cudaStreamWaitEvent failed"); rc = PNAE_ERR_CUDA; break; }
+            // this sweep reuses the workspace of step s - nws (nws <= nsets: and no output set younger than that)
+            if (s >= nws && cudaStreamWaitEvent(st, ev[2 * (s - nws) + 1], 0) != cudaSuccess) { pnae_set_error("cudaStreamWaitEvent failed"); rc = PNAE_ERR_CUDA; break; }
             if (fused) {
                 rc = launch_fwd("chamfer_graph_create_pipelined", b, n, xyz1[s], m, xyz2[s], dist1[k], idx1[k], dist2[k], idx2[k], nullptr,
                                 grad_xyz1[k], grad_xyz2[k], 0.f, 0.f, grad_dist1, grad_dist2, workspace[wk], workspace_bytes, st, ctas, fin, swept);

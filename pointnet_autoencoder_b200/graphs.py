@@ -25,8 +25,9 @@ class ChamferStep:
     def __init__(self, xyz1, xyz2, grad_dist1=None, grad_dist2=None, forward_only=False, share_buffers_with=None, outputs=None,
                  fused=False, pipelined=False):
         # pipelined (multi-step graphs): step s+1's sweep runs while step s's finalize / gradient resolve
-        # (pnae_chamfer_graph_create_pipelined).  Steps alternate between two output sets and two workspaces; the public
-        # attributes (.dist1 ...) are the set the LAST step wrote, `.other` holds the set of the step before it.
+        # (pnae_chamfer_graph_create_pipelined).  Steps cycle through three output sets and three workspaces; the public
+        # attributes (.dist1 ...) are the set the LAST step wrote, `.other` holds the set of the step before it and
+        # `.older` the one before that.
         # fused: NnDistance + NnDistanceGrad through pnae_nn_distance_fwd_grad (sweep + finalize, the finalize also
         # forms the gradients) instead of the three-kernel pnae_nn_distance_fwd -> pnae_nn_distance_bwd sequence
         self.fused = bool(fused) and not forward_only
@@ -70,27 +71,28 @@ class ChamferStep:
                 self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
             if self.pipelined:
                 if o is not None and getattr(o, "other", None) is not None:
-                    self.other = o.other
+                    self.other, self.older = o.other, o.older
                 else:
                     self.other = {k: torch.empty_like(getattr(self, k)) for k in names}
                     self.other["ws"] = torch.empty_like(self.ws)
+                    self.older = {k: torch.empty_like(v) for k, v in self.other.items()}
             else:
-                self.other = None
+                self.other = self.older = None
             torch.cuda.synchronize(dev)
             h = C.c_void_p()
             p = lambda t: C.c_void_p(t.data_ptr())
             arr1 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi1])
             arr2 = (C.c_void_p * self.steps)(*[t.data_ptr() for t in multi2])
             if self.pipelined:
-                last = (self.steps - 1) & 1          # the set the last step writes = the public attributes
+                last = (self.steps - 1) % 3          # the set the last step writes = the public attributes
                 def pair(k):
-                    mine, oth = (getattr(self, k) if k != "ws" else self.ws), self.other[k]
-                    sets = [oth, oth]
-                    sets[last] = mine
-                    return (C.c_void_p * 2)(sets[0].data_ptr(), sets[1].data_ptr())
+                    mine = getattr(self, k) if k != "ws" else self.ws
+                    sets = [None, None, None]
+                    sets[last] = mine; sets[(last - 1) % 3] = self.other[k]; sets[(last - 2) % 3] = self.older[k]
+                    return (C.c_void_p * 3)(*[t.data_ptr() for t in sets])
                 none2 = None
                 _lib.check(lib.pnae_chamfer_graph_create_pipelined(
-                    int(self.fused), self.steps, 2, b, n, arr1, m, arr2, pair("dist1"), pair("idx1"), pair("dist2"), pair("idx2"),
+                    int(self.fused), self.steps, 3, 3, b, n, arr1, m, arr2, pair("dist1"), pair("idx1"), pair("dist2"), pair("idx2"),
                     p(self.g1), p(self.g2), none2 if forward_only else pair("grad_xyz1"), none2 if forward_only else pair("grad_xyz2"),
                     pair("ws"), wsb, C.byref(h)))
                 self._h = h

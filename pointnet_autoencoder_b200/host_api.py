@@ -123,9 +123,9 @@ class ChamferHostPipeline:
             self.h_out = [torch.empty((k * stride,), dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
             self.h_in1 = [_pinned((k, b, n, 3), torch.float32) for _ in range(depth)]      # staging for non-pinned inputs
             self.h_in2 = [_pinned((k, b, m, 3), torch.float32) for _ in range(depth)]
-            # room for two workspaces: with several fused steps per submission the library then builds the software-pipelined
-            # graph (a step's sweep runs while the previous step's finalize resolves)
-            wsb = 2 * ((lib.pnae_nn_distance_workspace_bytes(b, n, m) + 255) // 256 * 256)
+            # room for three workspaces: with several fused steps per submission the library then builds the software-pipelined
+            # graph (a step's sweep runs while the previous steps' finalizes resolve)
+            wsb = 3 * ((lib.pnae_nn_distance_workspace_bytes(b, n, m) + 255) // 256 * 256)
             self.ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=self.device)
             arr = lambda ts: (C.c_void_p * depth)(*[t.data_ptr() for t in ts])
             h = C.c_void_p()

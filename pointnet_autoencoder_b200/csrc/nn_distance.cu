@@ -34,7 +34,10 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int kR = 8;                 // rows per lane (contiguous: lane l owns rows l*kR .. l*kR+kR-1 of the block)
+#ifndef PNAE_NN_ROWS
+#define PNAE_NN_ROWS 8
+#endif
+constexpr int kR = PNAE_NN_ROWS;      // rows per lane (contiguous: lane l owns rows l*kR .. l*kR+kR-1 of the block)
 constexpr int kRowsPerBlock = 32 * kR; // 256 rows per warp
 constexpr int kChunk = 32;            // columns per unit = columns per row-argmin tag
 constexpr int kWarps = 4;             // warps per CTA (independent; no CTA-wide barrier anywhere)
@@ -314,9 +317,12 @@ nn_fwd_kernel(const FwdParams p)
                         best[r] = min3f(best[r], d0[r], d1[r]);
                     }
                     // column minima over this lane's rows; d >= 0: unsigned order == float order
-                    static_assert(kR == 8, "column tree below is written for 8 rows per lane");
-                    bits[g] = __float_as_uint(fminf(min3f(min3f(min3f(d0[0], d0[1], d0[2]), d0[3], d0[4]), d0[5], d0[6]), d0[7]));
-                    bits[g + 1] = __float_as_uint(fminf(min3f(min3f(min3f(d1[0], d1[1], d1[2]), d1[3], d1[4]), d1[5], d1[6]), d1[7]));
+                    static_assert(kR % 2 == 0 && kR >= 4, "column tree below takes the rows two at a time");
+                    float c0 = min3f(d0[0], d0[1], d0[2]), c1 = min3f(d1[0], d1[1], d1[2]);
+#pragma unroll
+                    for (int r = 3; r + 1 < kR; r += 2) { c0 = min3f(c0, d0[r], d0[r + 1]); c1 = min3f(c1, d1[r], d1[r + 1]); }
+                    bits[g] = __float_as_uint(fminf(c0, d0[kR - 1]));
+                    bits[g + 1] = __float_as_uint(fminf(c1, d1[kR - 1]));
                 }
                 unsigned mn[kGroup], who[kGroup];
 #pragma unroll

@@ -78,6 +78,8 @@ def enc():
     wt = w.t().contiguous().to(torch.bfloat16)
     t = graph_time(lambda: ops.encoder_conv_pool(x, wt), reps=10)
     flop = 2.0 * b * n * k * c
+    to = graph_time(lambda: ops.encoder_conv_pool(x, wt, overlap=True), reps=10)
+    print("  ... as a programmatic dependent launch (PNAE_OVERLAP_PREVIOUS, the way the encoder chain enqueues it): %.2f us  %.1f TFLOP/s" % (to * 1e3, flop / (to * 1e-3) / 1e12))
     print("encoder conv5+pool (tcgen05)   %8.2f us  %7.1f TFLOP/s  (%.1f%% of the 1660.6 TF/s measured bf16 burst peak)" % (t * 1e3, flop / (t * 1e-3) / 1e12, 100 * flop / (t * 1e-3) / 1660.6e12))
     xf = x.float()
 

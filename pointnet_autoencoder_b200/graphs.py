@@ -65,6 +65,13 @@ class ChamferStep:
             self.grad_xyz1 = torch.empty((b, n, 3), **f32); self.grad_xyz2 = torch.empty((b, m, 3), **f32)
         self.pipelined = bool(pipelined) and self.steps >= 2
         names = ("dist1", "idx1", "dist2", "idx2", "grad_xyz1", "grad_xyz2")
+        if self.pipelined:
+            # the pipelined form needs the whole batch in one sweep launch (plan[3] = elements per launch): batches too
+            # large for that are captured strictly in order
+            plan = (C.c_int * 9)()
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            _lib.check(lib.pnae_nn_distance_plan(b, n, m, sms, plan))
+            self.pipelined = plan[3] >= b
         with torch.cuda.device(dev):
             wsb = lib.pnae_nn_distance_workspace_bytes(b, n, m)
             if o is None:

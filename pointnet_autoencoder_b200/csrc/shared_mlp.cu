@@ -458,15 +458,35 @@ mlp_apply_bf16_kernel(long long n4, int k, const float *__restrict__ in, const B
     pnae_pdl_wait();
     for (int c = threadIdx.x; c < k; c += blockDim.x) bn_fold_channel(bn, k, c, blockIdx.x == 0, s[c], t[c]);
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)((i * 4) % k);
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(in) + i);
-        const float a0 = fmaxf(fmaf(v.x, s[c], t[c]), 0.f), a1 = fmaxf(fmaf(v.y, s[c + 1], t[c + 1]), 0.f);
-        const float a2 = fmaxf(fmaf(v.z, s[c + 2], t[c + 2]), 0.f), a3 = fmaxf(fmaf(v.w, s[c + 3], t[c + 3]), 0.f);
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    auto emit = [&](long long i, const float4 &v, const float (&sc)[4], const float (&sh)[4]) {
+        const float a0 = fmaxf(fmaf(v.x, sc[0], sh[0]), 0.f), a1 = fmaxf(fmaf(v.y, sc[1], sh[1]), 0.f);
+        const float a2 = fmaxf(fmaf(v.z, sc[2], sh[2]), 0.f), a3 = fmaxf(fmaf(v.w, sc[3], sh[3]), 0.f);
         __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
         uint2 pk;
         pk.x = *reinterpret_cast<unsigned *>(&lo); pk.y = *reinterpret_cast<unsigned *>(&hi);
         reinterpret_cast<uint2 *>(out)[i] = pk;
+    };
+    if ((stride * 4) % k == 0) {
+        // the usual case (k divides 1024): a thread meets the same four channels on every trip, so their scale / shift
+        // live in registers and four loads are in flight per trip
+        const int c = (int)((i0 * 4) % k);
+        const float sc[4] = {s[c], s[c + 1], s[c + 2], s[c + 3]}, sh[4] = {t[c], t[c + 1], t[c + 2], t[c + 3]};
+        long long i = i0;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldg(reinterpret_cast<const float4 *>(in) + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; u++) emit(i + u * stride, v[u], sc, sh);
+        }
+        for (; i < n4; i += stride) emit(i, __ldg(reinterpret_cast<const float4 *>(in) + i), sc, sh);
+    } else {
+        for (long long i = i0; i < n4; i += stride) {
+            const int c = (int)((i * 4) % k);
+            const float sc[4] = {s[c], s[c + 1], s[c + 2], s[c + 3]}, sh[4] = {t[c], t[c + 1], t[c + 2], t[c + 3]};
+            emit(i, __ldg(reinterpret_cast<const float4 *>(in) + i), sc, sh);
+        }
     }
 }
 

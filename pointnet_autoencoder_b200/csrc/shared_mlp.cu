@@ -169,7 +169,10 @@ xyz_moments_kernel(long long npts, const float *__restrict__ xyz, double *__rest
 // TMEM, so the epilogue's stores overlap the next tile's MMAs.  Weights narrower than 128 channels are zero-padded.
 constexpr int kTcPoints = 256;                 // points per tile (UMMA N)
 constexpr int kTcM = 128;                      // channel rows of the weight operand (UMMA M)
-constexpr int kTcProducerWarps = 8, kTcEpiWarps = 4;
+#ifndef PNAE_TC_EPI_WARPS
+#define PNAE_TC_EPI_WARPS 4
+#endif
+constexpr int kTcProducerWarps = 8, kTcEpiWarps = PNAE_TC_EPI_WARPS;   // epilogue: one or two warps per TMEM lane quadrant
 constexpr int kTcThreads = 32 * (1 + kTcProducerWarps + kTcEpiWarps);
 constexpr uint32_t kTcWBytes = 2 * kTcM * 128;         // one weight operand (two 32-element k boxes)
 constexpr uint32_t kTcABytes = 2 * kTcPoints * 128;    // one activation operand
@@ -405,8 +408,10 @@ mlp_layer_tc_kernel(long long npts, const float *__restrict__ in, const FirstLay
             mbar_wait(t_full + buf, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (q * 32 < kout) {                                   // (warp-uniform) this quadrant holds real channels
+                constexpr int kPartsPerWarp = (kTcPoints / 64) / (kTcEpiWarps / 4);
+                const int part0 = ((warp - 1 - kTcProducerWarps) >> 2) * kPartsPerWarp;      // with two warps per quadrant: its half of the columns
 #pragma unroll 1
-                for (int part = 0; part < kTcPoints / 64; part++) {        // 64 columns at a time: two TMEM loads in flight
+                for (int part = part0; part < part0 + kPartsPerWarp; part++) {        // 64 columns at a time: two TMEM loads in flight
                     if (part * 64 >= valid) break;
                     uint32_t r[2][32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTcPoints + part * 64;

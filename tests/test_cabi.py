@@ -52,6 +52,46 @@ def test_argument_validation_without_compute():
     assert lib.pnae_nn_distance_fwd(0, 4, dummy, 4, dummy, dummy, dummy, dummy, dummy, None, 0, None) == 0
 
 
+def test_encoder_flags_and_pipelined_graph_arguments_are_checked_before_compute():
+    """The round-2 entry points reject unknown flag bits and malformed pointer lists without touching a device."""
+    lib = _lib.load()
+    d = C.c_void_p(256)                      # never dereferenced: every call below fails its argument checks first
+    bad = 8                                  # not PNAE_STATS_ZEROED (1) | PNAE_OVERLAP_PREVIOUS (2)
+    assert ops.STATS_ZEROED == 1 and ops.OVERLAP_PREVIOUS == 2
+    rc = lib.pnae_mlp_first(64, d, d, d, d, d, bad, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"flag" in lib.pnae_last_error()
+    rc = lib.pnae_mlp_layer(64, 64, 64, d, d, d, d, d, d, 1e-3, 0.9, 1, d, d, d, d, bad, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"flag" in lib.pnae_last_error()
+    rc = lib.pnae_mlp_layer(64, 64, 96, d, d, d, d, d, d, 1e-3, 0.9, 1, d, d, d, d, 0, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"64 or 128" in lib.pnae_last_error()
+    rc = lib.pnae_mlp_layer_xyz(64, d, d, d, d, d, d, d, d, 1e-3, 0.9, 1, 192, d, d, d, d, 0, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"64 or 128" in lib.pnae_last_error()
+    rc = lib.pnae_mlp_layer_xyz(64, d, None, d, d, d, d, d, d, 1e-3, 0.9, 1, 64, d, d, d, d, 0, None)     # training needs the moments
+    assert rc == _lib.PNAE_ERR_INVALID_ARG
+    rc = lib.pnae_xyz_moments(0, d, d, 0, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG
+    rc = lib.pnae_mlp_apply_bf16(64, 128, d, d, d, d, d, d, 1e-3, 0.9, 1, d, 1, None)                       # STATS_ZEROED means nothing here
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"flag" in lib.pnae_last_error()
+    rc = lib.pnae_encoder_conv_pool(2, 256, 128, 1024, d, d, d, d, d, d, None, None, 4, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"flag" in lib.pnae_last_error()
+    rc = lib.pnae_conv5_finish(2, 1024, 512.0, d, d, d, d, d, d, d, d, d, 1e-3, 0.9, 1, d, d, d, d, d, 5, None)
+    assert rc == _lib.PNAE_ERR_INVALID_ARG and b"flag" in lib.pnae_last_error()
+    # pipelined multi-step graph: at least two output sets, 2 <= workspaces <= sets, complete pointer lists
+    h = C.c_void_p()
+    one = (C.c_void_p * 1)(256)
+    three = (C.c_void_p * 3)(256, 512, 768)
+    hole = (C.c_void_p * 3)(256, None, 768)
+    args = lambda nsets, nws, outs, ws: (1, 4, nsets, nws, 2, 64, three, 64, three, outs, outs, outs, outs, d, d, outs, outs, ws, 1 << 20, C.byref(h))
+    assert lib.pnae_chamfer_graph_create_pipelined(*args(1, 1, one, one)) == _lib.PNAE_ERR_INVALID_ARG
+    assert lib.pnae_chamfer_graph_create_pipelined(*args(2, 3, three, three)) == _lib.PNAE_ERR_INVALID_ARG      # more workspaces than sets
+    assert lib.pnae_chamfer_graph_create_pipelined(*args(3, 3, hole, three)) == _lib.PNAE_ERR_INVALID_ARG
+    assert b"output set" in lib.pnae_last_error()
+    same = (C.c_void_p * 3)(256, 256, 256)
+    assert lib.pnae_chamfer_graph_create_pipelined(*args(3, 3, three, same)) == _lib.PNAE_ERR_INVALID_ARG
+    assert b"workspace" in lib.pnae_last_error()
+    assert not h.value
+
+
 def test_no_cpu_fallback():
     a = torch.zeros(2, 8, 3)
     with pytest.raises(RuntimeError, match="no CPU path"):

@@ -17,7 +17,9 @@
 //    27 exponentials per pair instead of 30.
 //  * the per-point epilogues (the divisions / clamps that produce ratioL, ratioR, remainL,
 //    remainR) are evaluated on the fly while a task stages its streamed points, from the
-//    previous sweep's partial sums -- no extra pass, no extra barrier.
+//    previous sweep's partial sums -- no extra pass, no extra barrier.  Staging is the job of
+//    dedicated producer warps working one task ahead into a double-buffered tile (named
+//    barriers): its dependent L2 round trips never stall the warps that feed the SFU.
 //  * the inner loop is packed FP32 (FFMA2/FADD2/FMUL2: two own points per thread share every
 //    instruction) feeding MUFU.EX2; on B200 the packed form lets the SFU run concurrently
 //    with the FMA pipe (profiles/r1_microbench_b200.txt: 9.5 vs 14.1 cycles per pair).
@@ -32,15 +34,29 @@ namespace cg = cooperative_groups;
 namespace {
 
 #ifndef PNAE_AM_THREADS
-#define PNAE_AM_THREADS 256
+#define PNAE_AM_THREADS 512
 #endif
 #ifndef PNAE_AM_TS
 #define PNAE_AM_TS 128
 #endif
 #ifndef PNAE_AM_CTAS
-#define PNAE_AM_CTAS 2
+#define PNAE_AM_CTAS 1
 #endif
-constexpr int kThreads = PNAE_AM_THREADS;
+// One CTA per SM: 16 compute warps that advance together (a barrier pair per task) plus 4 producer warps.  With two
+// CTAs of 8 warps per SM -- round 1's shape -- the two did not advance together: the hardware favoured one, which finished
+// a sweep after 39 us and then idled at the grid barrier while the other, alone and latency-bound, took until 56 us
+// (tools/am_trace.py).  Measured at B=32, N=M=2048 (ms): 2 x 256 threads 1.253; 512 + 64 producers 1.193; 512 + 128: 1.145,
+// with the pair loop unrolled 8x 1.135; 512 + 256: 1.151; streamed chunks of 64 / 256 points 1.213 / 1.283.
+#ifndef PNAE_AM_UNROLL
+#define PNAE_AM_UNROLL 8
+#endif
+#ifndef PNAE_AM_PRODUCERS
+#define PNAE_AM_PRODUCERS 128
+#endif
+constexpr int kInnerUnroll = PNAE_AM_UNROLL;
+constexpr int kThreads = PNAE_AM_THREADS;     // compute threads per CTA
+constexpr int kProd = PNAE_AM_PRODUCERS;      // producer threads per CTA: they stage the streamed points of the NEXT task
+constexpr int kCtaThreads = kThreads + kProd;
 constexpr int kOwn = 2 * kThreads;     // own points per task: one packed pair per thread
 constexpr int kTs = PNAE_AM_TS;        // streamed points per task
 constexpr int kCtasPerSm = PNAE_AM_CTAS;
@@ -118,8 +134,13 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 //   kB  : own l, stream k, w = ratioL_lev[k]                          -> ps0 = sumr (before * remainR)
 //   kCA : own k, stream l, w = ratioR_lev[l], v = remainR_{lev+1}[l]  -> ps0 = sumc_lev, ps1 = suml_{lev+1}
 //   kC  : as kCA without the A half (last real level)                 -> ps0 = sumc_lev
+// named barriers of the producer / consumer hand-off (0 is __syncthreads): one FULL and one EMPTY per tile buffer
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarCompute = 5;
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 template <int KIND>
-__device__ void sweep(const EmdParams &p, int lev, int stage, Rec *tile, float2 *tilev)
+__device__ void sweep(const EmdParams &p, int lev, int stage, Rec (*tiles)[kTs], float2 (*tilevs)[kTs])
 {
     const long long ctas = gridDim.x;
     const bool rowside = (KIND != kB);
@@ -135,50 +156,25 @@ __device__ void sweep(const EmdParams &p, int lev, int stage, Rec *tile, float2 
     const float c0 = pnae_level_scale(lev), c1 = pnae_level_scale(lev + 1);
     const float2 sc0 = f2(c0, c0), sc1 = f2(c1, c1);
 
-    long long t = (long long)blockIdx.x * g.tasks / ctas;
+    const long long t0 = (long long)blockIdx.x * g.tasks / ctas;
     const long long tend = ((long long)blockIdx.x + 1) * g.tasks / ctas;
     const int per_e = g.nob * g.nch;
 
-    int held_e = -1, held_ob = -1;
-    long long held_t0 = 0;
-    float2 nox = f2(0, 0), noy = f2(0, 0), noz = f2(0, 0), rl = f2(0, 0), acc0 = f2(0, 0), acc1 = f2(0, 0);
-    int own_i0 = 0, own_i1 = 0;
-
-    auto flush = [&]() {
-        const long long first = ((long long)held_e * g.nob + held_ob) * g.nch;
-        const int slot = (int)min((long long)blockIdx.x - owner_of(first, ctas, g.tasks), held_t0 - first);
-        const size_t base = ((size_t)held_e * p.nslot + slot) * p.maxnm;
-        if (own_i0 < g.nown) { out0[base + own_i0] = acc0.x; if (KIND == kCA) out1[base + own_i0] = acc1.x; }
-        if (own_i1 < g.nown) { out0[base + own_i1] = acc0.y; if (KIND == kCA) out1[base + own_i1] = acc1.y; }
-    };
-
-    for (; t < tend; t++) {
-        const int e = (int)(t / per_e);
-        const int r = (int)(t - (long long)e * per_e);
-        const int ob = r / g.nch, ch = r - ob * g.nch;
-        const float *oxyz = own_xyz + (size_t)e * g.nown * 3;
-        const float *sxyz = str_xyz + (size_t)e * g.nstr * 3;
-
-        if (e != held_e || ob != held_ob) {
-            if (held_e >= 0) flush();
-            held_e = e; held_ob = ob; held_t0 = t;
-            own_i0 = ob * kOwn + 2 * threadIdx.x; own_i1 = own_i0 + 1;
-            const int a = min(own_i0, g.nown - 1), c = min(own_i1, g.nown - 1);
-            nox = f2(-__ldg(oxyz + a * 3), -__ldg(oxyz + c * 3));
-            noy = f2(-__ldg(oxyz + a * 3 + 1), -__ldg(oxyz + c * 3 + 1));
-            noz = f2(-__ldg(oxyz + a * 3 + 2), -__ldg(oxyz + c * 3 + 2));
-            if (KIND == kCA || KIND == kC) {
-                // ratioL_lev[k] of the own points, written by the B sweep of this level
-                const float *fl = p.factors + ((size_t)e * kLevels + lev) * (p.n + p.m);
-                rl = f2(__ldcg(fl + a), __ldcg(fl + c));
-            }
-            acc0 = f2(0, 0); acc1 = f2(0, 0);
-        }
-
+    if (threadIdx.x >= kThreads) {
+        // ===== producers: stage task t's streamed points (and evaluate the previous sweep's epilogue for them) into tile
+        // buffer (t - t0) & 1 while the compute warps are still on task t - 1 =====
+        for (long long t = t0; t < tend; t++) {
+            const int it = (int)(t - t0), bufi = it & 1;
+            Rec *tile = tiles[bufi];
+            float2 *tilev = tilevs[bufi];
+            const int e = (int)(t / per_e);
+            const int r = (int)(t - (long long)e * per_e);
+            const int ob = r / g.nch, ch = r - ob * g.nch;
+            const float *sxyz = str_xyz + (size_t)e * g.nstr * 3;
+            if (it >= 2) bar_sync(kBarEmpty + bufi, kCtaThreads);            // the compute warps are through with this buffer
         // ---- stage the streamed chunk; evaluate the previous sweep's epilogue for its points
-        __syncthreads();
         const int s0 = ch * kTs;
-        for (int i = threadIdx.x; i < kTs; i += kThreads) {
+        for (int i = threadIdx.x - kThreads; i < kTs; i += kProd) {
             const int s = s0 + i;
             const bool valid = s < g.nstr;
             const int sc = valid ? s : g.nstr - 1;
@@ -219,10 +215,58 @@ __device__ void sweep(const EmdParams &p, int lev, int stage, Rec *tile, float2 
             tile[i] = rec;
             if (KIND == kCA) tilev[i] = f2(v, v);
         }
-        __syncthreads();
+
+            bar_arrive(kBarFull + bufi, kCtaThreads);
+        }
+        // the compute warps' last (at most two) EMPTY arrivals have no refill to wait for them: take them here, so every
+        // barrier is back at zero when the sweep ends
+        const int nt = (int)(tend - t0);
+        for (int it = nt > 2 ? nt - 2 : 0; it < nt; it++) bar_sync(kBarEmpty + (it & 1), kCtaThreads);
+        return;
+    }
+
+    // ===== compute warps =====
+    int held_e = -1, held_ob = -1;
+    long long held_t0 = 0;
+    float2 nox = f2(0, 0), noy = f2(0, 0), noz = f2(0, 0), rl = f2(0, 0), acc0 = f2(0, 0), acc1 = f2(0, 0);
+    int own_i0 = 0, own_i1 = 0;
+
+    auto flush = [&]() {
+        const long long first = ((long long)held_e * g.nob + held_ob) * g.nch;
+        const int slot = (int)min((long long)blockIdx.x - owner_of(first, ctas, g.tasks), held_t0 - first);
+        const size_t base = ((size_t)held_e * p.nslot + slot) * p.maxnm;
+        if (own_i0 < g.nown) { out0[base + own_i0] = acc0.x; if (KIND == kCA) out1[base + own_i0] = acc1.x; }
+        if (own_i1 < g.nown) { out0[base + own_i1] = acc0.y; if (KIND == kCA) out1[base + own_i1] = acc1.y; }
+    };
+
+    for (long long t = t0; t < tend; t++) {
+        const int bufi = (int)(t - t0) & 1;
+        const Rec *tile = tiles[bufi];
+        const float2 *tilev = tilevs[bufi];
+        const int e = (int)(t / per_e);
+        const int r = (int)(t - (long long)e * per_e);
+        const int ob = r / g.nch;
+        const float *oxyz = own_xyz + (size_t)e * g.nown * 3;
+        if (e != held_e || ob != held_ob) {
+            if (held_e >= 0) flush();
+            held_e = e; held_ob = ob; held_t0 = t;
+            own_i0 = ob * kOwn + 2 * threadIdx.x; own_i1 = own_i0 + 1;
+            const int a = min(own_i0, g.nown - 1), c = min(own_i1, g.nown - 1);
+            nox = f2(-__ldg(oxyz + a * 3), -__ldg(oxyz + c * 3));
+            noy = f2(-__ldg(oxyz + a * 3 + 1), -__ldg(oxyz + c * 3 + 1));
+            noz = f2(-__ldg(oxyz + a * 3 + 2), -__ldg(oxyz + c * 3 + 2));
+            if (KIND == kCA || KIND == kC) {
+                // ratioL_lev[k] of the own points, written by the B sweep of this level
+                const float *fl = p.factors + ((size_t)e * kLevels + lev) * (p.n + p.m);
+                rl = f2(__ldcg(fl + a), __ldcg(fl + c));
+            }
+            acc0 = f2(0, 0); acc1 = f2(0, 0);
+        }
+
+        bar_sync(kBarFull + bufi, kCtaThreads);                              // the producers have staged this task
 
         // ---- own pair x kTs streamed points, packed FP32
-#pragma unroll 4
+#pragma unroll kInnerUnroll
         for (int i = 0; i < kTs; i++) {
             const float4 r0 = *reinterpret_cast<const float4 *>(&tile[i].x0);
             const float4 r1 = *reinterpret_cast<const float4 *>(&tile[i].z0);
@@ -253,6 +297,7 @@ __device__ void sweep(const EmdParams &p, int lev, int stage, Rec *tile, float2 
                 }
             }
         }
+        bar_arrive(kBarEmpty + bufi, kCtaThreads);
     }
     if (held_e >= 0) flush();
 }
@@ -266,11 +311,11 @@ __device__ void last_level(const EmdParams &p, int stage, float *red)
     const Geo grow = make_geo(p.b, p.n, p.m);
     const float *in0 = p.ps0 + (size_t)((stage & 1) ^ 1) * p.b * p.nslot * p.maxnm;
     const int lev = kLevels - 1;
-    auto block_sum = [&](float v) -> float {
+    auto block_sum = [&](float v) -> float {      // (the compute warps only: the producers are not in here)
         v = warp_sum(v);
-        __syncthreads();
+        bar_sync(kBarCompute, kThreads);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-        __syncthreads();
+        bar_sync(kBarCompute, kThreads);
         float s = 0.f;
         for (int w = 0; w < kThreads / 32; w++) s += red[w];
         return s;
@@ -299,9 +344,9 @@ __device__ void last_level(const EmdParams &p, int stage, float *red)
     }
 }
 
-#ifdef PNAE_AM_TRACE                   // tuning builds only (tools/am_trace.py): SM-clock stamps of the sweeps and barriers
-__device__ long long g_am_trace[3][64];        // three CTAs: every sweep's start and end
-__device__ long long g_am_all[1024][4];        // per CTA: smid, duration of level 3's B sweep, of its C/A sweep
+#ifdef PNAE_AM_TRACE                   // tuning builds only (tools/am_trace.py): SM-clock stamps of one CTA's sweeps and barriers
+__device__ long long g_am_trace[3][64];
+__device__ long long g_am_all[1024][4];        // per CTA: smid, duration of level 3's B sweep, of its C/A sweep, tasks
 extern "C" __attribute__((visibility("default"))) int pnae_debug_am_trace(long long *host)
 {
     return (int)cudaMemcpyFromSymbol(host, g_am_trace, sizeof(g_am_trace));
@@ -310,23 +355,28 @@ extern "C" __attribute__((visibility("default"))) int pnae_debug_am_all(long lon
 {
     return (int)cudaMemcpyFromSymbol(host, g_am_all, sizeof(g_am_all));
 }
-#define AM_STAMP() do { if (trace_cta >= 0 && threadIdx.x == 0 && ti < 64) g_am_trace[trace_cta][ti] = clock64(); ti++; } while (0)
+#define AM_TRACE(i) do { if (trace_cta >= 0 && threadIdx.x == 0 && (i) < 64) g_am_trace[trace_cta][i] = clock64(); } while (0)
 #else
-#define AM_STAMP() do { } while (0)
+#define AM_TRACE(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 approx_match_kernel(const EmdParams p)
 {
 #ifdef PNAE_AM_TRACE
     const int trace_cta = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == gridDim.x - 1 ? 2 : -1;
     int ti = 0;
 #endif
-    __shared__ Rec tile[kTs];
-    __shared__ float2 tilev[kTs];
+    __shared__ Rec tile[2][kTs];                 // double-buffered: the producers stage one task ahead
+    __shared__ float2 tilev[2][kTs];
     __shared__ float red[kThreads / 32];
     cg::grid_group grid = cg::this_grid();
     int stage = 0;
+#ifdef PNAE_AM_TRACE
+#define AM_STAMP() do { AM_TRACE(ti); ti++; } while (0)
+#else
+#define AM_STAMP() do { } while (0)
+#endif
     AM_STAMP();
     sweep<kA0>(p, 0, stage++, tile, tilev);
     AM_STAMP();
@@ -335,13 +385,12 @@ approx_match_kernel(const EmdParams p)
     for (int lev = 0; lev < kLevels - 1; lev++) {
         AM_STAMP();
 #ifdef PNAE_AM_TRACE
-        const long long tb0 = clock64();
+        long long tb0 = clock64();
 #endif
         sweep<kB>(p, lev, stage++, tile, tilev);
 #ifdef PNAE_AM_TRACE
         if (lev == 3 && threadIdx.x == 0 && blockIdx.x < 1024) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             g_am_all[blockIdx.x][0] = smid; g_am_all[blockIdx.x][1] = clock64() - tb0;
         }
 #endif
@@ -350,7 +399,7 @@ approx_match_kernel(const EmdParams p)
         grid.sync();
         AM_STAMP();
 #ifdef PNAE_AM_TRACE
-        const long long tc0 = clock64();
+        long long tc0 = clock64();
 #endif
         if (lev < kLevels - 2) sweep<kCA>(p, lev, stage++, tile, tilev);
         else sweep<kC>(p, lev, stage++, tile, tilev);
@@ -362,7 +411,7 @@ approx_match_kernel(const EmdParams p)
         grid.sync();
     }
     AM_STAMP();
-    last_level(p, stage, red);
+    if (threadIdx.x < kThreads) last_level(p, stage, red);
     AM_STAMP();
 }
 
@@ -433,7 +482,7 @@ extern "C" int pnae_approx_match(int b, int n, int m, const float *xyz1, const f
     p.multiR = (n >= m) ? (float)(n / m) : 1.0f;
     cudaStream_t st = (cudaStream_t)stream;
     void *args[] = {(void *)&p};
-    PNAE_CUDA_OK(cudaLaunchCooperativeKernel((const void *)approx_match_kernel, dim3(pl.grid), dim3(kThreads), args, 0, st));
+    PNAE_CUDA_OK(cudaLaunchCooperativeKernel((const void *)approx_match_kernel, dim3(pl.grid), dim3(kCtaThreads), args, 0, st));
     if (match != nullptr) return pnae_match_from_factors_impl(b, n, m, xyz1, xyz2, factors, match, st);
     return PNAE_OK;
 }

@@ -189,7 +189,11 @@ def test_pipelined_graph_gives_every_step_the_sequential_results(mode, steps, b,
             assert torch.equal(got["dist2"], d2) and torch.equal(got["idx2"], i2)
             if mode != "forward_only":
                 g1, g2 = ops.nn_distance_bwd(x1[s], x2[s], step.g1, i1, step.g2, i2)
-                assert torch.allclose(got["grad_xyz1"], g1, rtol=1e-4, atol=1e-8) and torch.allclose(got["grad_xyz2"], g2, rtol=1e-4, atol=1e-8)
+                # the scattered half of a gradient is a sum of float atomics in no fixed order (as in the reference,
+                # tf_nndistance_g.cu:143-148): a point that collects a dozen nearly cancelling terms differs from run to
+                # run by a few ulps of the LARGEST term, so the absolute tolerance scales with the gradient's magnitude
+                for got_g, want_g in ((got["grad_xyz1"], g1), (got["grad_xyz2"], g2)):
+                    assert torch.allclose(got_g, want_g, rtol=1e-4, atol=4e-6 * float(want_g.abs().max()))
 
 
 def test_wide_index_span_arithmetic_matches_oracle():

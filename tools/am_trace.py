@@ -35,11 +35,13 @@ for cta in range(3):
 
 allb = np.zeros((1024, 4), np.int64)
 assert _lib.load().pnae_debug_am_all(allb.ctypes.data_as(ctypes.c_void_p)) == 0
-g = 296
+plan = (ctypes.c_int * 8)()
+assert _lib.load().pnae_approx_match_plan(b, n, n, torch.cuda.get_device_properties(0).multi_processor_count, plan) == 0
+g = plan[0]
 d = allb[:g]
 print("per-CTA duration of level 3's B sweep (us): min %.1f  median %.1f  max %.1f" % (d[:, 1].min() / 1.925e3, np.median(d[:, 1]) / 1.925e3, d[:, 1].max() / 1.925e3))
 print("CTA: smid B C/A (us)")
-for i in list(range(0, 12)) + list(range(140, 156)) + list(range(284, 296)):
+for i in list(range(0, 8)) + list(range(g // 2 - 4, g // 2 + 4)) + list(range(g - 8, g)):
     print("  %3d: sm %3d  %5.1f %5.1f" % (i, d[i, 0], d[i, 1] / 1.925e3, d[i, 2] / 1.925e3))
 # do the two CTAs of an SM finish together?
 from collections import defaultdict

@@ -151,13 +151,15 @@ def test_chamfer_graph_step_equals_eager_calls():
     g1, g2 = ops.nn_distance_bwd(x1, x2, step.g1, i1, step.g2, i2)
     assert torch.equal(step.dist1, d1) and torch.equal(step.idx1, i1)
     assert torch.equal(step.dist2, d2) and torch.equal(step.idx2, i2)
-    assert torch.allclose(step.grad_xyz1, g1, rtol=1e-5, atol=1e-9) and torch.allclose(step.grad_xyz2, g2, rtol=1e-5, atol=1e-9)
+    # (float atomics in no fixed order: the absolute tolerance scales with the gradient's magnitude)
+    close = lambda a, r, rtol: torch.allclose(a, r, rtol=rtol, atol=4e-6 * float(r.abs().max()))
+    assert close(step.grad_xyz1, g1, 1e-5) and close(step.grad_xyz2, g2, 1e-5)
     fstep = ChamferStep(x1, x2, fused=True)            # two-kernel form of the same step
     for _ in range(2):
         fstep.run()
     torch.cuda.synchronize()
     assert torch.equal(fstep.dist1, d1) and torch.equal(fstep.idx1, i1) and torch.equal(fstep.dist2, d2) and torch.equal(fstep.idx2, i2)
-    assert torch.allclose(fstep.grad_xyz1, g1, rtol=1e-4, atol=1e-8) and torch.allclose(fstep.grad_xyz2, g2, rtol=1e-4, atol=1e-8)
+    assert close(fstep.grad_xyz1, g1, 1e-4) and close(fstep.grad_xyz2, g2, 1e-4)
     # new data through the same graph
     other = x1.flip(0).contiguous()        # step.xyz1 aliases x1: take the new data before overwriting it
     step.xyz1.copy_(other)
